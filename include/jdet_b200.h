@@ -1,0 +1,101 @@
+/* jdet_b200.h — C ABI of libjdet_b200.so: JDet's oriented-box geometry hot path on B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  Each entry point replaces one `jt.code(...)` inline-op call site
+ * of the reference (Jittor/JDet @ 01974379, paths relative to python/jdet/); the binding a
+ * maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is DEVICE memory owned by the caller, fp32/int32 contiguous, unless it says "host";
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - nothing allocates, nothing synchronises, nothing touches the host: scratch comes from the
+ *     caller via (`workspace`, `workspace_bytes`), sized by the matching *_workspace_bytes();
+ *     all calls are CUDA-graph capturable;
+ *   - return value: 0 = ok; > 0 = a cudaError_t; JDET_ERR_* (< 0) = rejected arguments;
+ *   - angles are radians (ops/box_iou_rotated.py:56-59), boxes are [x_ctr, y_ctr, w, h, theta].
+ *   - there is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef JDET_B200_H_
+#define JDET_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JDET_ERR_BAD_ARG (-1)
+#define JDET_ERR_WORKSPACE (-2)
+#define JDET_ERR_UNSUPPORTED (-3)
+
+/* library / build identification: "jdet_b200 <version> sm_100a" */
+const char* jdet_version(void);
+
+/* ---- box_iou_rotated -------------------------------------------------------------------------
+ * replaces: box_iou_rotated()    ops/box_iou_rotated.py:502-509 (kernel :412-461, launch :464-485)
+ *           box_iou_rotated_v1() ops/box_iou_rotated_v1.py:507-525 (incl. the small-box zeroing :516-523)
+ * boxes1 (n1,5), boxes2 (n2,5) -> ious (n1,n2) row-major.  version: 0 | 1.                        */
+size_t jdet_box_iou_rotated_workspace_bytes(int n1, int n2);
+int jdet_box_iou_rotated(const float* boxes1, int n1, const float* boxes2, int n2, float* ious, int version,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- nms_rotated -----------------------------------------------------------------------------
+ * replaces: nms_rotated_cuda(dets, order_t, iou_threshold, box_length) ops/nms_rotated.py:506-513
+ *           (kernel :352-411, launch + host reduce :450-493).
+ * dets (n, box_length), box_length 5 = [x,y,w,h,theta] | 6 = [..., label]; order (n,) int32 indices by
+ * descending score; keep (n,) bytes, fully written, 1 = kept, indexed like dets.
+ * Strict `IoU > iou_threshold` (the reference CUDA path), IoU arguments (higher, lower).            */
+size_t jdet_nms_rotated_workspace_bytes(int n, int box_length);
+int jdet_nms_rotated(const float* dets, int n, int box_length, const int* order, float iou_threshold,
+                     unsigned char* keep, void* workspace, size_t workspace_bytes, void* stream);
+
+/* stable descending argsort (ties: lower index first)
+ * replaces: scores.argsort(0, descending=True) ops/nms_rotated.py:519,532                          */
+size_t jdet_argsort_desc_workspace_bytes(int n);
+int jdet_argsort_desc(const float* scores, int n, int* order, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ---- roi_align_rotated -----------------------------------------------------------------------
+ * replaces: version 1: _RotatedROIAlign_v1.execute ops/roi_align_rotated_v1.py:300-326 (kernel :70-147)
+ *           version 0: _RotatedROIAlign.execute    ops/roi_align_rotated.py:257-283   (kernel :60-127)
+ * input (B,C,H,W); rois (R,6) = [batch, x_ctr, y_ctr, w, h, theta]; output (R,C,PH,PW).
+ * sampling_ratio: the int the reference kernel receives (<= 0: adaptive ceil(roi/pooled) grid).    */
+size_t jdet_roi_align_rotated_workspace_bytes(int B, int C, int H, int W, int R, int PH, int PW,
+                                              int sampling_ratio);
+int jdet_roi_align_rotated(int version, const float* input, int B, int C, int H, int W, const float* rois,
+                           int R, int PH, int PW, float spatial_scale, int sampling_ratio, float* output,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- feature_refine (rotated_feature_align) --------------------------------------------------
+ * replaces: feature_refine_forward ops/fr.py:234-240 (kernel :114-165), FeatureRefineFunction.execute :257-264
+ * features (N,C,H,W); best_rbboxes (N,H,W,5); output (N,C,H,W); points: 1 | 5.                     */
+int jdet_feature_refine(const float* features, const float* best_rbboxes, int N, int C, int H, int W,
+                        int points, float spatial_scale, float* output, void* stream);
+
+/* ---- AlignConv / DeformConv v1 forward -------------------------------------------------------
+ * replaces: AlignConv.get_offset models/roi_heads/s2anet_head.py:677-713 (batched over images :716-721)
+ * anchors (N,H,W,5) image space -> offset (N, 2*k*k, H, W), channel 2t = dy, 2t+1 = dx, t = i*k + j */
+int jdet_align_conv_offset(const float* anchors, int N, int H, int W, float stride, int kernel_size,
+                           float* offset, void* stream);
+
+/* replaces: DeformConvFunction.execute / deform_conv_forward_cuda ops/dcn_v1.py:412-454, 561-600
+ *           (deformable_im2col_gpu_kernel :131-184 + jt.matmul :446-447; no columns tensor here).
+ * x (B,C,H,W); offset (B, dg*2*kh*kw, Ho, Wo); weight (Co, C/groups, kh, kw); out (B,Co,Ho,Wo).
+ * relu != 0 fuses AlignConv's ReLU (s2anet_head.py:722).                                           */
+int jdet_deform_conv_forward(const float* x, const float* offset, const float* weight, int B, int C, int H,
+                             int W, int Co, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w,
+                             int dil_h, int dil_w, int groups, int deformable_groups, int relu, float* out,
+                             void* stream);
+
+/* replaces: AlignConv.execute models/roi_heads/s2anet_head.py:715-723 as ONE fused call:
+ * offsets from anchors -> deformable 3x3 sampling -> tcgen05 GEMM (3xTF32 split, fp32-class
+ * accuracy) -> ReLU.  x (N,C,H,W); anchors (N,H,W,5); weight (Co,C,3,3); out (N,Co,H,W).
+ * Requires C % 32 == 0, Co % 16 == 0, Co <= 256.                                                    */
+size_t jdet_align_conv_forward_workspace_bytes(int N, int C, int H, int W, int Co);
+int jdet_align_conv_forward(const float* x, const float* anchors, const float* weight, int N, int C, int H,
+                            int W, int Co, float stride, float* out, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JDET_B200_H_ */

@@ -1,0 +1,106 @@
+// feature_refine.cu — rotated_feature_align ("feature_refine" in JDet) forward for sm_100a.
+//
+// Replaces feature_refine_forward_kernel + launch (/root/reference/python/jdet/ops/fr.py:114-165,
+// 234-240):  out[n,c,h,w] = in[n,c,h,w] + sum_{i<points} bilinear(in[n,c], py_i, px_i),
+// points in {1,5}; bbox (n,h,w,5): bbox[0]*scale is the ROW, bbox[1]*scale the COLUMN (:133-134).
+//
+// Reference shape of work: one thread per (n,c,h,w): the box is re-read and the 1/5 sample points
+// (cosf/sinf included) re-derived for every channel, 256x redundantly at the bench shape.
+// Here a thread owns one pixel: it decodes its box once into taps+weights held in registers, then
+// walks a slab of channels.  Consecutive lanes are consecutive pixels, so the centre read and the
+// store are 128-B coalesced and the taps of neighbouring pixels fall in the same few lines of the
+// plane (L1 hits).  HBM traffic ~ one read + one write of the feature map: an HBM-bound stream.
+//
+// Layout in HBM: features (N,C,H,W) fp32, boxes (N,H,W,5) fp32, out (N,C,H,W) fp32.
+#include "common.cuh"
+
+namespace jdet {
+
+struct Tap4 {
+  int o00, o01, o10, o11;
+  float w1, w2, w3, w4;
+};
+
+// fr.py:18-67
+__device__ __forceinline__ Tap4 fr_tap(float y, float x, int H, int W) {
+  Tap4 t;
+  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W || !(y == y) || !(x == x)) {
+    t.o00 = -1; t.o01 = t.o10 = t.o11 = 0;          // sample contributes exactly 0 (fr.py:24-26)
+    t.w1 = t.w2 = t.w3 = t.w4 = 0.f;
+    return t;
+  }
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+  const float ly = y - (float)yl, lx = x - (float)xl;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  t.o00 = yl * W + xl; t.o01 = yl * W + xh; t.o10 = yh * W + xl; t.o11 = yh * W + xh;
+  t.w1 = __fmul_rn(hy, hx); t.w2 = __fmul_rn(hy, lx); t.w3 = __fmul_rn(ly, hx); t.w4 = __fmul_rn(ly, lx);
+  return t;
+}
+
+// grid = (pixel tiles of 256, channel slabs, N)
+template <int POINTS>
+__global__ void __launch_bounds__(256) feature_refine_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
+                                                              int C, int H, int W, float spatial_scale, int ch_per_cta,
+                                                              float* __restrict__ out) {
+  const int HW = H * W;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
+  if (p >= HW) return;
+  const float* bb = boxes + ((size_t)n * HW + p) * 5;
+  const float roi_y = __fmul_rn(bb[0], spatial_scale), roi_x = __fmul_rn(bb[1], spatial_scale);
+  Tap4 taps[POINTS];
+  taps[0] = fr_tap(roi_y, roi_x, H, W);
+  if (POINTS > 1) {   // fr.py:139-153
+    const float rw = __fmul_rn(bb[2], spatial_scale), rh = __fmul_rn(bb[3], spatial_scale), ra = bb[4];
+    const float w2 = rw * 0.5f, h2 = rh * 0.5f;
+    const float ca = cosf(ra), sa = sinf(ra);
+    const float wx = __fmul_rn(ca, w2), wy = __fmul_rn(sa, w2), hx = __fmul_rn(-sa, h2), hy = __fmul_rn(ca, h2);
+    taps[1 % POINTS] = fr_tap(__fadd_rn(__fadd_rn(roi_y, wy), hy), __fadd_rn(__fadd_rn(roi_x, wx), hx), H, W);
+    taps[2 % POINTS] = fr_tap(__fadd_rn(__fsub_rn(roi_y, wy), hy), __fadd_rn(__fsub_rn(roi_x, wx), hx), H, W);
+    taps[3 % POINTS] = fr_tap(__fsub_rn(__fsub_rn(roi_y, wy), hy), __fsub_rn(__fsub_rn(roi_x, wx), hx), H, W);
+    taps[4 % POINTS] = fr_tap(__fsub_rn(__fadd_rn(roi_y, wy), hy), __fsub_rn(__fadd_rn(roi_x, wx), hx), H, W);
+  }
+  const float* plane = feat + ((size_t)n * C + c0) * HW;
+  float* dst = out + ((size_t)n * C + c0) * HW + p;
+#pragma unroll 4
+  for (int c = c0; c < c1; c++) {
+    float v = __ldg(plane + p);
+#pragma unroll
+    for (int i = 0; i < POINTS; i++) {
+      const Tap4& t = taps[i];
+      if (t.o00 >= 0)
+        v += t.w1 * __ldg(plane + t.o00) + t.w2 * __ldg(plane + t.o01) + t.w3 * __ldg(plane + t.o10) +
+           t.w4 * __ldg(plane + t.o11);
+    }
+    st_stream(dst, v);
+    plane += HW;
+    dst += HW;
+  }
+}
+
+}  // namespace jdet
+
+// jdet.ops.fr.feature_refine(features, best_rbboxes, spatial_scale, points) (ops/fr.py:255-273)
+JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxes, int N, int C, int H, int W,
+                                 int points, float spatial_scale, float* output, void* stream) {
+  using namespace jdet;
+  if (N < 0 || C < 0 || H < 0 || W < 0 || (points != 1 && points != 5)) return JDET_ERR_BAD_ARG;
+  if ((size_t)N * C * H * W == 0) return 0;
+  if (!features || !best_rbboxes || !output) return JDET_ERR_BAD_ARG;
+  if (N > 65535) return JDET_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W;
+  const int ptiles = jdet_ceil_div(HW, 256);
+  // enough CTAs to fill 148 SMs several times over, but keep slabs long enough to amortise the box decode
+  int ch_per_cta = C;
+  while (ch_per_cta > 16 && (long long)ptiles * jdet_ceil_div(C, ch_per_cta) * N < 148 * 8) ch_per_cta = (ch_per_cta + 1) / 2;
+  dim3 grid(ptiles, jdet_ceil_div(C, ch_per_cta), N);
+  if (points == 1) feature_refine_kernel<1><<<grid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, output);
+  else             feature_refine_kernel<5><<<grid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, output);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,294 @@
+// roi_align_rotated.cu — rotated RoIAlign forward (v0 and v1 conventions) for sm_100a.
+//
+// Replaces ROIAlignRotatedForward + launch snippets:
+//   version 1: /root/reference/python/jdet/ops/roi_align_rotated_v1.py:23-147, 300-326
+//   version 0: /root/reference/python/jdet/ops/roi_align_rotated.py:21-127, 257-283
+// The four convention differences (centre -0.5, rotation sign, "<0" vs "<=0" clamp, count max)
+// are template branches of one kernel family.
+//
+// Reference shape of work: one thread per output element; every thread re-derives the RoI
+// geometry (sincos included) and issues 16 scattered 4-byte loads into one NCHW plane, i.e. two
+// 32-B sectors per sample for 16 useful bytes.  Here the per-RoI work is hoisted:
+//
+//   sample table   per RoI, once: PH*PW*gh*gw sample points -> 4 tap offsets + 4 weights, in smem,
+//                  reused by every channel (256x at the bench shape).
+//   staged path    (dense RoI sets) the NCHW map is re-laid once as channel-last (B,H,W,C) in the
+//                  caller's workspace (tiled smem transpose, both sides coalesced); the gather
+//                  kernel then reads every tap as 16-B vectors over channels: a half-warp covers
+//                  256 contiguous bytes of one pixel.  Output slab (64 ch x PH*PW) is assembled
+//                  in smem and written with coalesced 16-B streaming stores.
+//   direct path    (few RoIs on a big map, where re-laying the map would cost more than it saves)
+//                  NCHW gathers with the hoisted table; lanes run along the bins of one channel.
+//
+// Layout in HBM: input (B,C,H,W) fp32; rois (R,6) = [batch, cx, cy, w, h, theta]; output
+// (R,C,PH,PW) fp32; workspace: channel-last copy (B*H*W*C fp32) for the staged path.
+#include "common.cuh"
+
+namespace jdet {
+
+constexpr int kMaxSamples = 1024;       // PH*PW*gh*gw held in smem per RoI; larger grids take the loop path
+
+struct SampleTap {
+  int o00, o01, o10, o11;               // pixel offsets (y*W + x), NOT scaled by channels; -1 => sample is out of range
+  float w1, w2, w3, w4;
+};
+
+struct RoiGeom {
+  int batch, gh, gw;
+  float cw, ch, bin_h, bin_w, start_h, start_w, ct, st, inv_count;
+};
+
+template <int VERSION>
+__device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float spatial_scale, int sample_num,
+                                            int PH, int PW) {
+  RoiGeom g;
+  g.batch = (int)roi[0];
+  if (VERSION == 1) {   // roi_align_rotated_v1.py:89-90
+    g.cw = __fsub_rn(__fmul_rn(roi[1], spatial_scale), 0.5f);
+    g.ch = __fsub_rn(__fmul_rn(roi[2], spatial_scale), 0.5f);
+  } else {              // roi_align_rotated.py:77-78
+    g.cw = __fmul_rn(roi[1], spatial_scale);
+    g.ch = __fmul_rn(roi[2], spatial_scale);
+  }
+  float rw = __fmul_rn(roi[3], spatial_scale), rh = __fmul_rn(roi[4], spatial_scale);
+  const float theta = roi[5];
+  rw = fmaxf(rw, 1.f);
+  rh = fmaxf(rh, 1.f);
+  g.bin_h = __fdiv_rn(rh, (float)PH);
+  g.bin_w = __fdiv_rn(rw, (float)PW);
+  g.gh = sample_num > 0 ? sample_num : (int)ceilf(__fdiv_rn(rh, (float)PH));
+  g.gw = sample_num > 0 ? sample_num : (int)ceilf(__fdiv_rn(rw, (float)PW));
+  g.start_h = -rh * 0.5f;
+  g.start_w = -rw * 0.5f;
+  // one sincos per RoI instead of one per output element; correctly-rounded via double
+  const double th = (double)theta;
+  g.ct = (float)cos(th);
+  g.st = (float)sin(th);
+  const int cnt = g.gh * g.gw;
+  g.inv_count = (VERSION == 1) ? (float)max(cnt, 1) : (float)cnt;   // divisor, applied with a true division
+  return g;
+}
+
+// sample point -> taps/weights, following bilinear_interpolate (v1.py:23-68 / .py:21-56)
+template <int VERSION>
+__device__ __forceinline__ SampleTap make_tap(const RoiGeom& g, int ph, int pw, int iy, int ix, int H, int W) {
+  // same operation order as the reference; explicit _rn ops so no FMA contraction moves a
+  // sample across a pixel or validity boundary
+  const float yy = __fadd_rn(__fadd_rn(g.start_h, __fmul_rn((float)ph, g.bin_h)),
+                             __fdiv_rn(__fmul_rn((float)iy + .5f, g.bin_h), (float)g.gh));
+  const float xx = __fadd_rn(__fadd_rn(g.start_w, __fmul_rn((float)pw, g.bin_w)),
+                             __fdiv_rn(__fmul_rn((float)ix + .5f, g.bin_w), (float)g.gw));
+  float x, y;
+  if (VERSION == 1) {
+    x = __fadd_rn(__fadd_rn(__fmul_rn(xx, g.ct), __fmul_rn(yy, g.st)), g.cw);
+    y = __fadd_rn(__fsub_rn(__fmul_rn(yy, g.ct), __fmul_rn(xx, g.st)), g.ch);
+  } else {
+    x = __fadd_rn(__fsub_rn(__fmul_rn(xx, g.ct), __fmul_rn(yy, g.st)), g.cw);
+    y = __fadd_rn(__fadd_rn(__fmul_rn(xx, g.st), __fmul_rn(yy, g.ct)), g.ch);
+  }
+  SampleTap t;
+  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W || !(y == y) || !(x == x)) {
+    // (NaN coordinates: the reference's comparisons are all false and it then indexes with
+    //  (int)NaN; that is undefined behaviour there — here such samples contribute 0.)
+    t.o00 = t.o01 = t.o10 = t.o11 = -1;
+    t.w1 = t.w2 = t.w3 = t.w4 = 0.f;
+    return t;
+  }
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+  const float ly = y - (float)yl, lx = x - (float)xl;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  t.o00 = yl * W + xl; t.o01 = yl * W + xh; t.o10 = yh * W + xl; t.o11 = yh * W + xh;
+  t.w1 = __fmul_rn(hy, hx); t.w2 = __fmul_rn(hy, lx); t.w3 = __fmul_rn(ly, hx); t.w4 = __fmul_rn(ly, lx);
+  return t;
+}
+
+// ---- NCHW -> NHWC re-layout --------------------------------------------------------------------
+// in: (B, C, HW)   out: (B, HW, C).  32x32 tiles through padded smem; both sides 128-B coalesced.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const float* src = in + (size_t)b * C * HW;
+  float* dst = out + (size_t)b * C * HW;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int c = c0 + ty + 8 * k, p = p0 + tx;
+    if (c < C && p < HW) tile[ty + 8 * k][tx] = __ldg(src + (size_t)c * HW + p);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int p = p0 + ty + 8 * k, c = c0 + tx;
+    if (c < C && p < HW) dst[(size_t)p * C + c] = tile[tx][ty + 8 * k];
+  }
+}
+
+// ---- staged gather kernel ----------------------------------------------------------------------
+// grid = (R, C/64 slabs); 256 threads.  Requires C % 64 == 0 and PH*PW*gh*gw <= kMaxSamples
+// (sampling_ratio > 0).  Thread task = (bin, channel quad): 16 lanes span the slab's 64 channels.
+template <int VERSION>
+__global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const float* __restrict__ feat_nhwc,
+                                                              const float* __restrict__ rois, int C, int H, int W,
+                                                              int PH, int PW, float spatial_scale, int sample_num,
+                                                              float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int nbins = PH * PW;
+  const int r = blockIdx.x, c0 = blockIdx.y * 64;
+  __shared__ RoiGeom g;
+  if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)r * 6, spatial_scale, sample_num, PH, PW);
+  __syncthreads();
+  const int spb = g.gh * g.gw;                       // samples per bin
+  SampleTap* taps = reinterpret_cast<SampleTap*>(smem);
+  float* s_out = reinterpret_cast<float*>(taps + nbins * spb);   // [64][nbins]
+  for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
+    const int bin = s / spb, k = s - bin * spb;
+    taps[s] = make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
+  }
+  __syncthreads();
+  const float* base = feat_nhwc + (size_t)g.batch * H * W * C + c0;
+  const int q = threadIdx.x & 15;                   // channel quad within the slab
+  for (int bin = threadIdx.x >> 4; bin < nbins; bin += blockDim.x >> 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const SampleTap* tp = taps + bin * spb;
+    for (int k = 0; k < spb; k++) {
+      const SampleTap t = tp[k];
+      if (t.o00 < 0) continue;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o00 * C) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o01 * C) + q);
+      const float4 c = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o10 * C) + q);
+      const float4 d = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o11 * C) + q);
+      acc.x += t.w1 * a.x + t.w2 * b.x + t.w3 * c.x + t.w4 * d.x;
+      acc.y += t.w1 * a.y + t.w2 * b.y + t.w3 * c.y + t.w4 * d.y;
+      acc.z += t.w1 * a.z + t.w2 * b.z + t.w3 * c.z + t.w4 * d.z;
+      acc.w += t.w1 * a.w + t.w2 * b.w + t.w3 * c.w + t.w4 * d.w;
+    }
+    const float cnt = g.inv_count;
+    s_out[(4 * q + 0) * nbins + bin] = acc.x / cnt;
+    s_out[(4 * q + 1) * nbins + bin] = acc.y / cnt;
+    s_out[(4 * q + 2) * nbins + bin] = acc.z / cnt;
+    s_out[(4 * q + 3) * nbins + bin] = acc.w / cnt;
+  }
+  __syncthreads();
+  // out[r][c0 .. c0+63][bins] is one contiguous run of 64*nbins floats
+  float* dst = out + ((size_t)r * C + c0) * nbins;
+  const int total = 64 * nbins;
+  if ((total & 3) == 0 && ((((size_t)r * C + c0) * nbins) & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < total; i += blockDim.x * 4)
+      st_stream_v4(dst + i, s_out[i], s_out[i + 1], s_out[i + 2], s_out[i + 3]);
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) st_stream(dst + i, s_out[i]);
+  }
+}
+
+// ---- direct NCHW kernel --------------------------------------------------------------------------
+// grid = (R, channel chunks); thread task = (channel, bin); taps from the per-RoI table when it fits,
+// otherwise recomputed per element (adaptive sampling grids of huge RoIs).
+template <int VERSION>
+__global__ void __launch_bounds__(256) roi_align_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
+                                                              int C, int H, int W, int PH, int PW, float spatial_scale,
+                                                              int sample_num, int ch_per_cta, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int nbins = PH * PW;
+  const int r = blockIdx.x, c0 = blockIdx.y * ch_per_cta;
+  const int c1 = min(C, c0 + ch_per_cta);
+  __shared__ RoiGeom g;
+  if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)r * 6, spatial_scale, sample_num, PH, PW);
+  __syncthreads();
+  const int spb = g.gh * g.gw;
+  const bool tabled = (long long)nbins * spb <= kMaxSamples;
+  SampleTap* taps = reinterpret_cast<SampleTap*>(smem);
+  if (tabled) {
+    for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
+      const int bin = s / spb, k = s - bin * spb;
+      taps[s] = make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
+    }
+    __syncthreads();
+  }
+  const size_t plane = (size_t)H * W;
+  const float* fb = feat + (size_t)g.batch * C * plane;
+  const int total = (c1 - c0) * nbins;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c = c0 + i / nbins, bin = i % nbins;
+    const float* p = fb + (size_t)c * plane;
+    float acc = 0.f;
+    if (tabled) {
+      const SampleTap* tp = taps + bin * spb;
+      for (int k = 0; k < spb; k++) {
+        const SampleTap t = tp[k];
+        if (t.o00 < 0) continue;
+        acc += t.w1 * __ldg(p + t.o00) + t.w2 * __ldg(p + t.o01) + t.w3 * __ldg(p + t.o10) + t.w4 * __ldg(p + t.o11);
+      }
+    } else {
+      const int ph = bin / PW, pw = bin % PW;
+      for (int iy = 0; iy < g.gh; iy++)
+        for (int ix = 0; ix < g.gw; ix++) {
+          const SampleTap t = make_tap<VERSION>(g, ph, pw, iy, ix, H, W);
+          if (t.o00 < 0) continue;
+          acc += t.w1 * __ldg(p + t.o00) + t.w2 * __ldg(p + t.o01) + t.w3 * __ldg(p + t.o10) + t.w4 * __ldg(p + t.o11);
+        }
+    }
+    out[((size_t)r * C + c) * nbins + bin] = acc / g.inv_count;
+  }
+}
+
+static bool use_staged(int B, int C, int H, int W, int R, int PH, int PW, int sample_num) {
+  if (sample_num <= 0 || C % 64 != 0) return false;
+  if ((long long)PH * PW * sample_num * sample_num > kMaxSamples) return false;
+  // re-laying the map moves 8*B*C*H*W bytes; it pays once the RoI set samples the map densely
+  return (long long)R * PH * PW * sample_num * sample_num * 8 >= (long long)B * H * W;
+}
+
+}  // namespace jdet
+
+JDET_API size_t jdet_roi_align_rotated_workspace_bytes(int B, int C, int H, int W, int R, int PH, int PW,
+                                                       int sampling_ratio) {
+  if (!jdet::use_staged(B, C, H, W, R, PH, PW, sampling_ratio)) return 256;
+  return jdet_align_up((size_t)B * C * H * W * sizeof(float), 256);
+}
+
+// version 1: ROIAlignRotated_v1 / roi_align (ops/roi_align_rotated_v1.py:300-326,355-365)
+// version 0: ROIAlignRotated    / roi_align (ops/roi_align_rotated.py:257-283,312-322)
+// input (B,C,H,W), rois (R,6), output (R,C,PH,PW): device fp32 contiguous.  sampling_ratio is the
+// integer the reference's int parameter receives (Python side truncates the float like C does).
+JDET_API int jdet_roi_align_rotated(int version, const float* input, int B, int C, int H, int W, const float* rois,
+                                    int R, int PH, int PW, float spatial_scale, int sampling_ratio, float* output,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace jdet;
+  if ((version != 0 && version != 1) || B < 0 || C < 0 || H < 0 || W < 0 || R < 0 || PH <= 0 || PW <= 0)
+    return JDET_ERR_BAD_ARG;
+  if (R == 0 || C == 0) return 0;
+  if (!input || !rois || !output || B == 0 || H == 0 || W == 0) return JDET_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nbins = PH * PW;
+  if (use_staged(B, C, H, W, R, PH, PW, sampling_ratio)) {
+    const size_t need = jdet_align_up((size_t)B * C * H * W * sizeof(float), 256);
+    if (!workspace || workspace_bytes < need) return JDET_ERR_WORKSPACE;
+    float* nhwc = (float*)workspace;
+    dim3 tg(jdet_ceil_div(H * W, 32), jdet_ceil_div(C, 32), B);
+    nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(input, nhwc, C, H * W);
+    const size_t smem = (size_t)nbins * sampling_ratio * sampling_ratio * sizeof(SampleTap) + (size_t)64 * nbins * 4;
+    dim3 grid(R, C / 64);
+    if (version == 1) {
+      if (smem > 48 * 1024) JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_align_nhwc_kernel<1><<<grid, 256, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);
+    } else {
+      if (smem > 48 * 1024) JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_align_nhwc_kernel<0><<<grid, 256, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);
+    }
+  } else {
+    const int ch_per_cta = 32;
+    const size_t smem = (size_t)kMaxSamples * sizeof(SampleTap);
+    dim3 grid(R, jdet_ceil_div(C, ch_per_cta));
+    if (version == 1)
+      roi_align_nchw_kernel<1><<<grid, 256, smem, st>>>(input, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, ch_per_cta, output);
+    else
+      roi_align_nchw_kernel<0><<<grid, 256, smem, st>>>(input, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, ch_per_cta, output);
+  }
+  return (int)cudaGetLastError();
+}

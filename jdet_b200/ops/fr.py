@@ -1,0 +1,71 @@
+"""jdet.ops.fr mirror — feature_refine / FR / FeatureRefineModule (reference: python/jdet/ops/fr.py:255-347).
+
+feature_refine is R3Det's rotated feature alignment: out = in + sum_i bilinear(in, point_i), the points
+being the box centre (points=1) or centre + 4 corners (points=5).  Forward only.
+"""
+import torch
+from torch import nn
+
+from ._common import check, f32c, lib, require_cuda, stream_ptr
+
+
+def feature_refine(features, best_rbboxes, spatial_scale, points=1):
+    assert points in [1, 5]                                    # fr.py:261
+    require_cuda(features, best_rbboxes)
+    x, b = f32c(features), f32c(best_rbboxes)
+    N, C, H, W = x.shape
+    assert b.numel() == N * H * W * 5, "best_rbboxes must be (N,H,W,5) (or (N*H*W,5))"
+    out = torch.empty_like(x)
+    if out.numel() == 0:
+        return out
+    with torch.cuda.device(x.device):
+        check(lib().jdet_feature_refine(x.data_ptr(), b.data_ptr(), N, C, H, W, points, float(spatial_scale),
+                                        out.data_ptr(), stream_ptr(x.device)), "feature_refine")
+    return out
+
+
+class FR(nn.Module):
+    def __init__(self, spatial_scale, points=1):
+        super().__init__()
+        self.spatial_scale = float(spatial_scale)
+        self.points = points
+
+    def forward(self, features, best_rbboxes):
+        return feature_refine(features, best_rbboxes, self.spatial_scale, self.points)
+
+    execute = forward
+
+    def __repr__(self):
+        return self.__class__.__name__ + '(spatial_scale={}, points={})'.format(self.spatial_scale, self.points)
+
+
+class FeatureRefineModule(nn.Module):
+    """fr.py:291-347: conv_5_1(conv_1_5(x)) + conv_1_1(x) -> FR -> x + refined, per FPN level."""
+
+    def __init__(self, in_channels, featmap_strides, conv_cfg=None, norm_cfg=None):
+        super().__init__()
+        self.in_channels = in_channels
+        self.featmap_strides = featmap_strides
+        self.conv_cfg = conv_cfg
+        self.norm_cfg = norm_cfg
+        self.fr = nn.ModuleList([FR(spatial_scale=1 / s) for s in featmap_strides])
+        self.conv_5_1 = nn.Conv2d(in_channels, in_channels, kernel_size=(5, 1), stride=1, padding=(2, 0))
+        self.conv_1_5 = nn.Conv2d(in_channels, in_channels, kernel_size=(1, 5), stride=1, padding=(0, 2))
+        self.conv_1_1 = nn.Conv2d(in_channels, in_channels, kernel_size=1)
+        self.init_weights()
+
+    def init_weights(self):
+        for m in (self.conv_5_1, self.conv_1_5, self.conv_1_1):
+            nn.init.normal_(m.weight, mean=0.0, std=0.01)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0.0)
+
+    def forward(self, x, best_rbboxes):
+        mlvl_rbboxes = [torch.cat(best_rbbox) for best_rbbox in zip(*best_rbboxes)]
+        out = []
+        for x_scale, best_rbboxes_scale, fr_scale in zip(x, mlvl_rbboxes, self.fr):
+            feat_scale = self.conv_5_1(self.conv_1_5(x_scale)) + self.conv_1_1(x_scale)
+            out.append(x_scale + fr_scale(feat_scale, best_rbboxes_scale))
+        return out
+
+    execute = forward

@@ -1,0 +1,106 @@
+"""jdet.ops.nms_rotated mirror (reference: python/jdet/ops/nms_rotated.py:495-596).
+
+All entry points keep the reference names, argument order and return conventions:
+  nms_rotated(dets, scores, iou_threshold)                     -> kept indices, ascending   (:527-538)
+  ml_nms_rotated(dets, scores, labels, iou_threshold)          -> kept indices, ascending   (:515-525)
+  multiclass_nms_rotated(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1,
+                         score_factors=None)                   -> ((k,6) dets, (k,) labels) (:540-596)
+  nms_rotated_cuda(dets, order_t, iou_threshold, box_length=6) -> (n,) bool keep mask       (:506-513)
+Indices are int64 (torch idiom; the reference returns int32 — same values).
+"""
+import torch
+
+from ._common import check, f32c, lib, require_cuda, scratch, stream_ptr
+
+
+def argsort_desc(scores):
+    """Stable descending argsort on the device (ties keep the lower index first), int32."""
+    require_cuda(scores)
+    s = f32c(scores).reshape(-1)
+    n = s.numel()
+    order = torch.empty((n,), dtype=torch.int32, device=s.device)
+    if n == 0:
+        return order
+    L = lib()
+    with torch.cuda.device(s.device):
+        ws = scratch(L.jdet_argsort_desc_workspace_bytes(n), s.device)
+        check(L.jdet_argsort_desc(s.data_ptr(), n, order.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  stream_ptr(s.device)), "argsort_desc")
+    return order
+
+
+def nms_rotated_cuda(dets, order_t, iou_threshold, box_length=6):
+    """keep mask (n,) bool.  dets (n, box_length): [x,y,w,h,theta(,label)]; order_t: indices by
+    descending score.  Strict `IoU > iou_threshold`, as the reference CUDA kernel (:403-404)."""
+    require_cuda(dets, order_t)
+    d = f32c(dets)
+    assert d.dim() == 2 and d.shape[1] == box_length and box_length in (5, 6)
+    n = d.shape[0]
+    keep = torch.empty((n,), dtype=torch.bool, device=d.device)
+    if n == 0:
+        return keep
+    order = order_t.to(torch.int32).contiguous()
+    assert order.numel() == n
+    L = lib()
+    with torch.cuda.device(d.device):
+        ws = scratch(L.jdet_nms_rotated_workspace_bytes(n, box_length), d.device)
+        check(L.jdet_nms_rotated(d.data_ptr(), n, box_length, order.data_ptr(), float(iou_threshold),
+                                 keep.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(d.device)), "nms_rotated")
+    return keep
+
+
+def nms_rotated_cpu(dets, order_t, iou_threshold, box_length=6):
+    raise NotImplementedError("jdet_b200 has no CPU path (the reference's is ops/nms_rotated.py:495-504); "
+                              "use nms_rotated_cuda")
+
+
+def ml_nms_rotated(dets, scores, labels, iou_threshold):
+    assert dets.numel() > 0 and dets.dim() == 2              # nms_rotated.py:516
+    assert dets.dtype == scores.dtype                         # :517
+    require_cuda(dets, scores, labels)
+    d = torch.cat([f32c(dets), labels.to(torch.float32).unsqueeze(1)], dim=1)
+    order_t = argsort_desc(scores)
+    keep = nms_rotated_cuda(d, order_t, iou_threshold, box_length=6)
+    return torch.where(keep)[0]
+
+
+def nms_rotated(dets, scores, iou_threshold):
+    if dets.numel() == 0:                                     # :528-529
+        return torch.zeros((0,), dtype=torch.int64, device=dets.device)
+    assert dets.numel() > 0 and dets.dim() == 2
+    assert dets.dtype == scores.dtype
+    require_cuda(dets, scores)
+    order_t = argsort_desc(scores)
+    keep = nms_rotated_cuda(f32c(dets), order_t, iou_threshold, box_length=5)
+    return torch.where(keep)[0]
+
+
+def multiclass_nms_rotated(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None):
+    """NMS for multi-class rotated boxes; column 0 of multi_scores is background and ignored.
+    Returns ((k,6) [box, score], (k,) 0-based labels).  `max_num=-1` drops the lowest-scoring
+    detection, exactly like the reference (:590-591)."""
+    num_classes = multi_scores.size(1) - 1
+    if multi_bboxes.shape[1] > 5:
+        bboxes = multi_bboxes.view(multi_scores.size(0), -1, 5)[:, 1:]
+    else:
+        bboxes = multi_bboxes[:, None].expand(multi_bboxes.shape[0], num_classes, 5)
+    scores = multi_scores[:, 1:]
+    valid_mask = scores > score_thr
+    bboxes = bboxes[valid_mask]
+    if score_factors is not None:
+        scores = scores * score_factors[:, None]
+    scores = scores[valid_mask]
+    labels = valid_mask.nonzero()[:, 1]
+    if bboxes.numel() == 0:
+        return (torch.zeros((0, 6), device=multi_bboxes.device),
+                torch.zeros((0,), dtype=torch.int32, device=multi_bboxes.device))
+    nms_cfg_ = nms_cfg.copy()
+    nms_cfg_.pop('type', 'nms')
+    iou_thr = nms_cfg_.pop('iou_thr', 0.1)
+    keep = ml_nms_rotated(bboxes, scores, labels, iou_thr)
+    bboxes, scores, labels = bboxes[keep], scores[keep], labels[keep]
+    inds = torch.argsort(scores, descending=True, stable=True)
+    if keep.size(0) > max_num:
+        inds = inds[:max_num]
+    bboxes, scores, labels = bboxes[inds], scores[inds], labels[inds]
+    return torch.cat([bboxes, scores[:, None]], 1), labels

@@ -1,0 +1,56 @@
+"""jdet.ops.roi_align_rotated_v1 mirror (reference: python/jdet/ops/roi_align_rotated_v1.py:300-365).
+
+v1 convention (used by OrientedSingleRoIExtractor / Oriented R-CNN): centre shifted by -0.5,
+x = xx*cos + yy*sin, clamp on `< 0`, count = max(grid, 1).  Forward only (backward: later round).
+"""
+import torch
+from torch import nn
+
+from ._common import check, f32c, lib, require_cuda, scratch, stream_ptr
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+def _roi_align_impl(version, input, rois, output_size, spatial_scale, sampling_ratio):
+    assert rois.shape[1] == 6                                  # roi_align_rotated_v1.py:306
+    require_cuda(input, rois)
+    x, r = f32c(input), f32c(rois)
+    assert x.dim() == 4
+    ph, pw = _pair(output_size)
+    B, C, H, W = x.shape
+    R = r.shape[0]
+    out = torch.empty((R, C, ph, pw), dtype=torch.float32, device=x.device)
+    if out.numel() == 0:
+        return out
+    sr = int(sampling_ratio)        # the reference passes a float constant to an int parameter (truncation)
+    L = lib()
+    with torch.cuda.device(x.device):
+        ws = scratch(L.jdet_roi_align_rotated_workspace_bytes(B, C, H, W, R, ph, pw, sr), x.device)
+        check(L.jdet_roi_align_rotated(version, x.data_ptr(), B, C, H, W, r.data_ptr(), R, ph, pw,
+                                       float(spatial_scale), sr, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       stream_ptr(x.device)), "roi_align_rotated")
+    return out
+
+
+def roi_align(input, rois, output_size, spatial_scale, sampling_ratio):
+    """_RotatedROIAlign_v1.apply: input (B,C,H,W), rois (R,6)=[batch,cx,cy,w,h,theta] -> (R,C,PH,PW)."""
+    return _roi_align_impl(1, input, rois, output_size, spatial_scale, sampling_ratio)
+
+
+class ROIAlignRotated_v1(nn.Module):
+    def __init__(self, output_size, spatial_scale, sampling_ratio=0):
+        super().__init__()
+        self.output_size = _pair(output_size)
+        self.spatial_scale = spatial_scale
+        self.sampling_ratio = sampling_ratio
+
+    def forward(self, input, rois):
+        return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio)
+
+    execute = forward   # Jittor's name for forward
+
+    def __repr__(self):
+        return (self.__class__.__name__ + "(output_size=" + str(self.output_size) + ", spatial_scale=" +
+                str(self.spatial_scale) + ", sampling_ratio=" + str(self.sampling_ratio) + ")")

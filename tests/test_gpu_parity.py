@@ -1,0 +1,372 @@
+"""GPU parity tests: every C-ABI entry point against the oracle (oracle/oracle.cpp), the committed
+golden vectors and — where oracle/_ref/libref_cuda.so travelled to the box — the reference's own
+CUDA kernels on the same GPU.
+
+Bars (BASELINE.json north_star): IoU and NMS bit-exact against the oracle's CUDA-variant
+arithmetic; sampled features <= 1e-4 abs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import _refcuda
+from _inputs import ADVERSARIAL, clustered_boxes, dota_boxes, s2anet_anchors, tie_free_scores
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-4   # abs tolerance for sampled features / IoU floats (north_star)
+
+
+def cu(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def ops():
+    import jdet_b200.ops as o
+    return o
+
+
+# ------------------------------------------------------------------------------------ IoU
+@pytest.mark.parametrize("version", [0, 1])
+@pytest.mark.parametrize("shape", [(700, 900), (257, 131), (1, 1), (65, 4)])
+def test_iou_bit_exact_vs_oracle(version, shape):
+    rng = np.random.default_rng(11 + version)
+    n1, n2 = shape
+    b1 = np.concatenate([dota_boxes(rng, n1, 400.0), clustered_boxes(rng, n1 // 2 + 1, 10, 400.0), ADVERSARIAL])[:max(n1, 1)]
+    b2 = np.concatenate([ADVERSARIAL, dota_boxes(rng, n2, 400.0), b1[: n1 // 3]])[:max(n2, 1)]
+    fn = ops().box_iou_rotated if version == 0 else ops().box_iou_rotated_v1
+    got = fn(cu(b1), cu(b2)).cpu().numpy()
+    want = oracle.box_iou_rotated(b1, b2, version, oracle.VARIANT_CUDA)
+    bad = np.nonzero(bits(got) != bits(want))
+    assert len(bad[0]) == 0, (len(bad[0]), got[bad][:5], want[bad][:5])
+
+
+def test_iou_golden_and_known_answers():
+    g = np.load(os.path.join(GOLD, "ref_cpu_iou.npz"))
+    b1, b2 = cu(g["boxes1"]), cu(g["boxes2"])
+    for ver, fn in ((0, ops().box_iou_rotated), (1, ops().box_iou_rotated_v1)):
+        got = fn(b1, b2).cpu().numpy()
+        want = g["iou_v%d_cudavariant" % ver].copy()
+        if ver == 1:   # the fixture holds the raw kernel output; the Python post-pass zeroes small boxes
+            want[np.minimum(g["boxes1"][:, 2], g["boxes1"][:, 3]) < 1e-3, :] = 0
+            want[:, np.minimum(g["boxes2"][:, 2], g["boxes2"][:, 3]) < 1e-3] = 0
+        assert np.array_equal(bits(got), bits(want))
+        # reference CPU build (std::sort hull): same values up to hull tie-breaking
+        assert np.abs(got - np.where(want == 0, 0, g["iou_v%d_cpu" % ver])).max() <= 1e-6
+    k = np.load(os.path.join(GOLD, "known_answers.npz"))
+    got = ops().box_iou_rotated(cu(k["k1_boxes"]), cu(k["k1_boxes"])).cpu().numpy()
+    assert np.array_equal(bits(got), bits(k["k1_iou"]))
+    got = ops().box_iou_rotated(cu(k["k3_a"][None]), cu(k["k3_b"][None])).cpu().numpy()
+    assert got[0, 0] == k["k3_iou"]
+
+
+def test_iou_empty_and_dtype():
+    o = ops()
+    e = torch.zeros((0, 5), device="cuda")
+    b = cu(ADVERSARIAL)
+    assert o.box_iou_rotated(e, b).shape == (0, len(ADVERSARIAL))
+    assert o.box_iou_rotated(b, e).shape == (len(ADVERSARIAL), 0)
+    with pytest.raises(AssertionError):
+        o.box_iou_rotated(b, b.double())
+
+
+@pytest.mark.skipif(not _refcuda.available(), reason="oracle/_ref/libref_cuda.so not present")
+@pytest.mark.parametrize("version", [0, 1])
+def test_iou_vs_reference_cuda_kernel(version):
+    rng = np.random.default_rng(5)
+    b1 = cu(np.concatenate([dota_boxes(rng, 1000), clustered_boxes(rng, 500, 10)]))
+    b2 = cu(np.concatenate([dota_boxes(rng, 1000), clustered_boxes(rng, 300, 10)]))
+    fn = ops().box_iou_rotated if version == 0 else ops().box_iou_rotated_v1
+    got, ref = fn(b1, b2), _refcuda.box_iou_rotated(b1, b2, version)
+    # the reference kernel is compiled with nvcc's default FMA contraction: last-bit differences only
+    assert (got - ref).abs().max().item() <= 1e-5
+    assert ((got > 0) != (ref > 0)).sum().item() == 0
+
+
+def test_iou_full_size_properties():
+    """16k x 16k (1 GiB of IoUs): size-independent properties + spot checks against the oracle."""
+    rng = np.random.default_rng(0)
+    n = 16384
+    b = dota_boxes(rng, n)
+    tb = cu(b)
+    m = ops().box_iou_rotated(tb, tb)
+    d = m.diagonal()
+    assert (d - 1).abs().max().item() <= 2e-6                      # IoU(b,b) = 1
+    assert m.min().item() >= 0 and m.max().item() <= 1 + 1e-6
+    assert (m - m.t()).abs().max().item() <= 1e-5                   # symmetric up to rounding
+    ii, jj = rng.integers(0, n, 4000), rng.integers(0, n, 4000)
+    nz = torch.nonzero(m[:2048] > 0).cpu().numpy()[:4000]
+    ii, jj = np.concatenate([ii, nz[:, 0]]), np.concatenate([jj, nz[:, 1]])
+    got = m[torch.as_tensor(ii).cuda(), torch.as_tensor(jj).cuda()].cpu().numpy()
+    want = np.array([oracle.single_iou(b[i], b[j]) for i, j in zip(ii, jj)], np.float32)
+    assert np.array_equal(bits(got), bits(want))
+
+
+# ------------------------------------------------------------------------------------ NMS
+def _nms_case(rng, n, ncls, clustered=True):
+    d = clustered_boxes(rng, n, 25, 512.0) if clustered else dota_boxes(rng, n, 512.0)
+    return d, tie_free_scores(rng, n), rng.integers(0, ncls, n).astype(np.int64)
+
+
+@pytest.mark.parametrize("thr", [0.1, 0.3, 0.5])
+@pytest.mark.parametrize("n,ncls", [(3000, 5), (777, 1), (130, 40), (64, 2), (65, 3), (1, 1)])
+def test_ml_nms_bit_exact_vs_oracle(n, ncls, thr):
+    rng = np.random.default_rng(n + ncls)
+    d, s, l = _nms_case(rng, n, ncls)
+    got = ops().nms_rotated.ml_nms_rotated(cu(d), cu(s), cu(l, torch.int64), thr).cpu().numpy()
+    want = oracle.ml_nms_rotated(d, s, l, thr, oracle.VARIANT_CUDA)
+    assert np.array_equal(got, want)
+    got5 = ops().nms_rotated.nms_rotated(cu(d), cu(s), thr).cpu().numpy()
+    assert np.array_equal(got5, oracle.nms_rotated(d, s, thr, oracle.VARIANT_CUDA))
+
+
+def test_nms_golden_and_k2():
+    g = np.load(os.path.join(GOLD, "ref_cpu_nms.npz"))
+    d6, order = g["dets6"], cu(g["order"], torch.int32)
+    nr = ops().nms_rotated
+    for thr in (0.1, 0.3, 0.5):
+        for bl, d in ((5, d6[:, :5]), (6, d6)):
+            keep = nr.nms_rotated_cuda(cu(d), order, thr, box_length=bl).cpu().numpy()
+            assert np.array_equal(keep, g["keep%d_cpu_thr%02d" % (bl, int(thr * 10))])
+    k = np.load(os.path.join(GOLD, "known_answers.npz"))
+    assert nr.ml_nms_rotated(cu(k["k2_dets"]), cu(k["k2_scores"]), cu(k["k2_labels"], torch.int64), 0.3).tolist() == [2]
+    assert nr.nms_rotated(cu(k["k2_dets"]), cu(k["k2_scores"]), 0.3).tolist() == [2]
+    assert nr.ml_nms_rotated(cu(k["k2_dets"]), cu(k["k2_scores"]), cu([0, 1, 2], torch.int64), 0.3).tolist() == [0, 1, 2]
+
+
+def test_nms_strict_threshold_and_corner_cases():
+    nr = ops().nms_rotated
+    d = cu([[0, 0, 2, 2, 0], [0, 0, 2, 1, 0]])                   # IoU exactly 0.5
+    s = cu([0.9, 0.8])
+    assert nr.nms_rotated(d, s, 0.5).tolist() == [0, 1]          # strict >, the CUDA path (nms_rotated.py:403-404)
+    assert nr.nms_rotated(d, s, 0.4999).tolist() == [0]
+    # negative threshold: 0 > thr, so even disjoint / cross-class boxes suppress (reference semantics)
+    rng = np.random.default_rng(1)
+    dd, ss, ll = _nms_case(rng, 200, 3)
+    got = nr.ml_nms_rotated(cu(dd), cu(ss), cu(ll, torch.int64), -0.5).cpu().numpy()
+    assert np.array_equal(got, oracle.ml_nms_rotated(dd, ss, ll, -0.5, oracle.VARIANT_CUDA))
+    assert len(got) == 1
+    # ties in score: stable order, lower index first
+    st = np.full(200, 0.5, np.float32)
+    got = nr.ml_nms_rotated(cu(dd), cu(st), cu(ll, torch.int64), 0.2).cpu().numpy()
+    assert np.array_equal(got, oracle.ml_nms_rotated(dd, st, ll, 0.2, oracle.VARIANT_CUDA))
+    # degenerate boxes never suppress nor get suppressed
+    deg = np.array([[5, 5, 0, 0, 0], [5, 5, 0, 0, 0], [5, 5, 3, 3, 0], [5, 5, 3, 3, 0.01]], np.float32)
+    assert nr.nms_rotated(cu(deg), cu([0.9, 0.8, 0.7, 0.6]), 0.1).tolist() == [0, 1, 2]
+
+
+def test_multiclass_nms_rotated_matches_oracle():
+    rng = np.random.default_rng(21)
+    n, C = 1500, 15
+    boxes = clustered_boxes(rng, n, 30, 512.0)
+    scores = rng.random((n, C + 1)).astype(np.float32) ** 4
+    nr = ops().nms_rotated
+    for max_num in (-1, 2000, 100):
+        gd, gl = nr.multiclass_nms_rotated(cu(boxes), cu(scores), 0.05, dict(type="nms_rotated", iou_thr=0.1), max_num)
+        wd, wl = oracle.multiclass_nms_rotated(boxes, scores, 0.05, dict(iou_thr=0.1), max_num)
+        assert gd.shape == wd.shape and np.array_equal(gd.cpu().numpy(), wd) and np.array_equal(gl.cpu().numpy(), wl)
+    # per-class boxes (n, 5*(C+1)) layout and the empty return
+    mb = np.tile(boxes, (1, C + 1)).astype(np.float32)
+    gd, gl = nr.multiclass_nms_rotated(cu(mb), cu(scores), 0.05, dict(iou_thr=0.1), 50)
+    wd, wl = oracle.multiclass_nms_rotated(mb, scores, 0.05, dict(iou_thr=0.1), 50)
+    assert np.array_equal(gd.cpu().numpy(), wd) and np.array_equal(gl.cpu().numpy(), wl)
+    gd, gl = nr.multiclass_nms_rotated(cu(boxes), cu(scores), 2.0, dict(iou_thr=0.1))
+    assert gd.shape == (0, 6) and gl.shape == (0,)
+
+
+@pytest.mark.skipif(not _refcuda.available(), reason="oracle/_ref/libref_cuda.so not present")
+def test_nms_vs_reference_cuda_kernel_100k():
+    """BASELINE cfg3: 100k proposals x 15 classes, thr 0.1 — keep mask equal to the reference CUDA path."""
+    rng = np.random.default_rng(0)
+    n = 100000
+    d = np.concatenate([clustered_boxes(rng, n // 2, 50), dota_boxes(rng, n - n // 2)])
+    s, l = tie_free_scores(rng, n), rng.integers(0, 15, n)
+    d6 = cu(np.concatenate([d, l[:, None].astype(np.float32)], 1))
+    nr = ops().nms_rotated
+    order = nr.argsort_desc(cu(s))
+    assert np.array_equal(order.cpu().numpy(), oracle.argsort_desc(s))
+    keep = nr.nms_rotated_cuda(d6, order, 0.1, box_length=6).cpu().numpy()
+    ref, _ = _refcuda.nms_rotated_keep(d6, order, 0.1)
+    assert np.array_equal(keep, ref), int((keep != ref).sum())
+    # size-independent properties: survivors of one class are pairwise below threshold;
+    # NMS is idempotent on its own output
+    kept = np.nonzero(keep)[0]
+    kd, ks, kl = d[kept], s[kept], l[kept]
+    again = nr.ml_nms_rotated(cu(kd), cu(ks), cu(kl, torch.int64), 0.1).cpu().numpy()
+    assert np.array_equal(again, np.arange(len(kept)))
+    c0 = kd[kl == 0][:4000]
+    m = ops().box_iou_rotated(cu(c0), cu(c0))
+    m.fill_diagonal_(0)
+    assert m.max().item() <= 0.1 + 1e-6
+
+
+# ------------------------------------------------------------------------------------ RoIAlign
+def _rois(rng, R, B, extent, lo=8, hi=256):
+    b = dota_boxes(rng, R, extent, lo, hi)
+    return np.concatenate([rng.integers(0, B, (R, 1)).astype(np.float32), b], 1)
+
+
+@pytest.mark.parametrize("version", [0, 1])
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, C=64, H=40, W=56, R=300, out=(7, 7), sr=2, scale=0.25),      # staged (channel-last) path
+    dict(B=1, C=128, H=32, W=32, R=200, out=(5, 3), sr=3, scale=0.125),    # staged, non-square bins
+    dict(B=2, C=24, H=40, W=56, R=100, out=(7, 7), sr=2, scale=0.25),      # direct path (C % 64 != 0)
+    dict(B=2, C=64, H=64, W=64, R=3, out=(7, 7), sr=2, scale=0.0625),      # direct path (few RoIs)
+    dict(B=1, C=16, H=48, W=48, R=40, out=(7, 7), sr=0, scale=0.25),       # adaptive grid (sampling_ratio 0)
+])
+def test_roi_align_vs_oracle(version, cfg):
+    rng = np.random.default_rng(cfg["R"] + version)
+    x = rng.standard_normal((cfg["B"], cfg["C"], cfg["H"], cfg["W"])).astype(np.float32)
+    extent = cfg["W"] / cfg["scale"]
+    rois = _rois(rng, cfg["R"], cfg["B"], extent, 8, extent / 2)
+    rois[:5, 1:3] = [[-20, -20], [extent + 30, 5], [0, 0], [extent, extent], [extent / 2, -3]]   # border / outside
+    rois[5, 3:5] = [1.0, 1.0]                                                                    # malformed -> 1x1
+    mod = ops().roi_align_rotated_v1 if version == 1 else ops().roi_align_rotated
+    got = mod.roi_align(cu(x), cu(rois), cfg["out"], cfg["scale"], cfg["sr"]).cpu().numpy()
+    want = oracle.roi_align_rotated(x, rois, cfg["out"], cfg["scale"], cfg["sr"], version)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= TOL, np.abs(got - want).max()
+    if _refcuda.available():
+        ref = _refcuda.roi_align_rotated(cu(x), cu(rois), cfg["out"], cfg["scale"], cfg["sr"], version).cpu().numpy()
+        assert np.abs(got - ref).max() <= TOL, np.abs(got - ref).max()
+
+
+def test_roi_align_module_and_reference_selftest_shape():
+    """ops/roi_align_rotated_v1.py:376-386: feature (2,1024,64,64), the two literal RoIs, 7x7, 1/16."""
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2, 1024, 64, 64)).astype(np.float32)
+    rois = np.array([[0, 20, 120, 80, 195.5, 0.3], [1, 23, 56, 200, 300.5, 0.2]], np.float32)
+    for mod, cls, ver in ((ops().roi_align_rotated_v1, "ROIAlignRotated_v1", 1), (ops().roi_align_rotated, "ROIAlignRotated", 0)):
+        layer = getattr(mod, cls)((7, 7), 1 / 16.)
+        got = layer(cu(x), cu(rois)).cpu().numpy()
+        want = oracle.roi_align_rotated(x, rois, (7, 7), 1 / 16., 0, ver)
+        assert got.shape == (2, 1024, 7, 7) and np.abs(got - want).max() <= TOL
+        assert layer.execute(cu(x), cu(rois)).shape == (2, 1024, 7, 7)
+
+
+def test_roi_align_full_size_cfg2():
+    """BASELINE cfg2: 256-ch 256x256 map, 2048 RoIs, 7x7, sampling 2 — whole output vs the oracle."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((1, 256, 256, 256)).astype(np.float32)
+    rois = _rois(rng, 2048, 1, 1024.0)
+    got = ops().roi_align_rotated_v1.roi_align(cu(x), cu(rois), (7, 7), 0.25, 2).cpu().numpy()
+    want = oracle.roi_align_rotated(x, rois, (7, 7), 0.25, 2, 1)
+    err = np.abs(got - want)
+    assert err.max() <= TOL, err.max()
+
+
+# ------------------------------------------------------------------------------------ feature_refine
+@pytest.mark.parametrize("points", [1, 5])
+def test_feature_refine_vs_oracle(points):
+    rng = np.random.default_rng(points)
+    N, C, H, W, stride = 2, 48, 32, 40, 8.0
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    a = s2anet_anchors(rng, N, H, W, stride)
+    boxes = a[..., [1, 0, 2, 3, 4]].copy()       # the op reads bbox[0] as the row coordinate
+    boxes[0, 0, :8, :2] = [[-50, -50]] * 4 + [[1e4, 3]] * 4     # out-of-map samples
+    got = ops().fr.feature_refine(cu(x), cu(boxes), 1 / stride, points).cpu().numpy()
+    want = oracle.feature_refine(x, boxes, 1 / stride, points)
+    assert np.abs(got - want).max() <= TOL, np.abs(got - want).max()
+    if _refcuda.available():
+        ref = _refcuda.feature_refine(cu(x), cu(boxes), 1 / stride, points).cpu().numpy()
+        assert np.abs(got - ref).max() <= TOL
+    fr = ops().fr.FR(1 / stride, points)
+    assert np.array_equal(fr(cu(x), cu(boxes)).cpu().numpy(), got)
+
+
+def test_feature_refine_module():
+    rng = np.random.default_rng(9)
+    m = ops().fr.FeatureRefineModule(16, [8, 16]).cuda()
+    feats = [cu(rng.standard_normal((2, 16, 16, 16))), cu(rng.standard_normal((2, 16, 8, 8)))]
+    boxes = [[cu(s2anet_anchors(rng, 1, 16, 16, 8).reshape(-1, 5)), cu(s2anet_anchors(rng, 1, 8, 8, 16).reshape(-1, 5))]
+             for _ in range(2)]
+    with torch.no_grad():
+        out = m(feats, boxes)
+    assert [tuple(o.shape) for o in out] == [(2, 16, 16, 16), (2, 16, 8, 8)]
+
+
+# ------------------------------------------------------------------------------------ DeformConv / AlignConv
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, C=16, H=12, W=14, Co=24, k=3, stride=1, pad=1, dil=1, groups=1, dg=1),
+    dict(B=1, C=8, H=15, W=13, Co=12, k=3, stride=2, pad=1, dil=2, groups=1, dg=2),
+    dict(B=3, C=6, H=9, W=9, Co=70, k=1, stride=1, pad=0, dil=1, groups=1, dg=1),
+])
+def test_deform_conv_vs_oracle(cfg):
+    rng = np.random.default_rng(cfg["Co"])
+    B, C, H, W, Co, k = cfg["B"], cfg["C"], cfg["H"], cfg["W"], cfg["Co"], cfg["k"]
+    Ho = (H + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    Wo = (W + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    off = (rng.standard_normal((B, cfg["dg"] * 2 * k * k, Ho, Wo)) * 2).astype(np.float32)
+    w = (rng.standard_normal((Co, C, k, k)) * 0.2).astype(np.float32)
+    got = ops().dcn_v1.deform_conv(cu(x), cu(off), cu(w), cfg["stride"], cfg["pad"], cfg["dil"], cfg["groups"],
+                                   cfg["dg"]).cpu().numpy()
+    want = oracle.deform_conv(x, off, w, cfg["stride"], cfg["pad"], cfg["dil"], cfg["dg"])
+    assert np.abs(got - want).max() <= TOL, np.abs(got - want).max()
+    if _refcuda.available():
+        ref = _refcuda.deform_conv(cu(x), cu(off), cu(w), cfg["stride"], cfg["pad"], cfg["dil"], cfg["dg"]).cpu().numpy()
+        assert np.abs(got - ref).max() <= TOL
+
+
+def test_deform_conv_groups_match_per_group_oracle():
+    rng = np.random.default_rng(4)
+    B, C, H, W, Co, g = 2, 8, 10, 10, 12, 2
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    off = rng.standard_normal((B, 18, H, W)).astype(np.float32)
+    w = (rng.standard_normal((Co, C // g, 3, 3)) * 0.2).astype(np.float32)
+    got = ops().dcn_v1.deform_conv(cu(x), cu(off), cu(w), 1, 1, 1, g, 1).cpu().numpy()
+    for gi in range(g):
+        want = oracle.deform_conv(x[:, gi * 4:(gi + 1) * 4], off, w[gi * 6:(gi + 1) * 6], 1, 1, 1, 1)
+        assert np.abs(got[:, gi * 6:(gi + 1) * 6] - want).max() <= TOL
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16, 64, 8), (1, 256, 32, 32, 256, 16), (2, 32, 9, 7, 48, 32)])
+def test_align_conv_vs_oracle(shape):
+    N, C, H, W, Co, stride = shape
+    rng = np.random.default_rng(C + H)
+    from jdet_b200.models.roi_heads.s2anet_head import AlignConv
+    m = AlignConv(C, Co, 3).cuda()
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    a = s2anet_anchors(rng, N, H, W, stride)
+    w = m.deform_conv.weight.detach().cpu().numpy()
+    got = m(cu(x), cu(a), stride).cpu().numpy()
+    want = oracle.align_conv(x, a, stride, w)
+    assert got.shape == (N, Co, H, W) and (got >= 0).all()
+    assert np.abs(got - want).max() <= TOL, np.abs(got - want).max()
+    off = m.get_offset_batched(cu(a), stride).cpu().numpy()
+    assert np.abs(off - oracle.align_conv_offset(a, stride)).max() <= 1e-4
+    assert np.array_equal(m.get_offset(cu(a[0].reshape(-1, 5)), (H, W), stride).cpu().numpy(), off[0])
+
+
+# ------------------------------------------------------------------------------------ callers
+def test_roi_extractor_and_iou_calculator():
+    rng = np.random.default_rng(6)
+    from jdet_b200.models.roi_extractors import OrientedSingleRoIExtractor, RboxSingleRoIExtractor
+    from jdet_b200.models.boxes import BboxOverlaps2D_rotated, BboxOverlaps2D_rotated_v1
+    strides = [4, 8, 16, 32]
+    feats = [rng.standard_normal((2, 64, 256 // s, 256 // s)).astype(np.float32) for s in strides]
+    rois = _rois(rng, 400, 2, 256.0, 8, 200)
+    ext = OrientedSingleRoIExtractor(dict(type="ROIAlignRotated_v1", output_size=7, sampling_ratio=2), 64, strides,
+                                     extend_factor=(1.4, 1.2))
+    got = ext([cu(f) for f in feats], cu(rois)).cpu().numpy()
+    r2 = rois.copy()
+    r2[:, 3] *= 1.2
+    r2[:, 4] *= 1.4
+    lvl = np.clip(np.floor(np.log2(np.sqrt(r2[:, 3] * r2[:, 4]) / 56 + 1e-6)), 0, 3).astype(int)
+    want = np.zeros_like(got)
+    for i, s in enumerate(strides):
+        if (lvl == i).any():
+            want[lvl == i] = oracle.roi_align_rotated(feats[i], r2[lvl == i], 7, 1 / s, 2, 1)
+    assert np.abs(got - want).max() <= TOL
+    ext0 = RboxSingleRoIExtractor(dict(type="ROIAlignRotated", output_size=7, sampling_ratio=2), 64, strides)
+    assert ext0([cu(f) for f in feats], cu(rois)).shape == (400, 64, 7, 7)
+    b = dota_boxes(rng, 50, 200.0)
+    b6 = np.concatenate([b, rng.random((50, 1)).astype(np.float32)], 1)
+    assert np.array_equal(BboxOverlaps2D_rotated()(cu(b6), cu(b)).cpu().numpy(), oracle.box_iou_rotated(b, b, 0))
+    assert np.array_equal(BboxOverlaps2D_rotated_v1()(cu(b), cu(b6)).cpu().numpy(), oracle.box_iou_rotated(b, b, 1))
