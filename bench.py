@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — JDet oriented-box geometry hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extra]
+
+Headline (BASELINE.json `metric`, quoted on configs[1]): rotated RoIs/s of roi_align_rotated on a
+256-ch 256x256 FPN map with 2048 RoIs, 7x7 bins, sampling_ratio 2.  A "step" is one pass of that
+op over one synthetic 1024^2-tile's RoI batch.  `value` is measured with inputs resident in HBM,
+`e2e` through the public op with pinned HOST buffers (H2D + op + D2H inside the timed region).
+The second half of the metric (rNMS boxes/s, configs[2]) and the other hot-path ops are reported in
+`extra`, each with its own roofline line.  N > 1: one process per GPU (torchrun), each rank runs the
+same per-GPU workload on its own tile (weak scaling, no data-path collective in the headline op);
+the NMS leg all-gathers padded final detections over NCCL.
+
+`--impl reference` times the reference's CPU implementation of the same path on the host cores:
+roi_align_rotated has NO CPU path in the reference (CUDA-only), so this arm runs the oracle port
+(`kind: port`, OpenMP over RoIs) on a bounded RoI sample per step.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+L2_FLUSH_BYTES = 256 << 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"} \
+            if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else \
+            {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+             nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def time_steps(torch, fn, steps, warmup, flush, sampler=None):
+    """W warm-ups, then K steps; every step is bracketed by CUDA events on the current stream, the
+    L2 flush sits OUTSIDE the events.  Returns total device milliseconds over the K steps."""
+    for _ in range(warmup):
+        flush()
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx = sampler if sampler is not None else _Null()
+    with ctx:
+        for a, b in ev:
+            flush()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+    return float(sum(a.elapsed_time(b) for a, b in ev))
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+
+# ------------------------------------------------------------------------------------------------
+def make_cfg2(seed):
+    from _inputs import dota_boxes
+    rng = np.random.default_rng(seed)
+    rois = np.concatenate([np.zeros((2048, 1), np.float32), dota_boxes(rng, 2048, 1024.0)], 1)
+    return rois
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import jdet_b200.ops as ops
+    from jdet_b200 import dist as jdist
+    peaks = load_peaks()
+    flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    flush = lambda: flush_buf.zero_()
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- headline: roi_align_rotated_v1, cfg2 -------------------------------------------------
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    feat = torch.randn((1, 256, 256, 256), device=dev, generator=g)
+    rois_h = make_cfg2(rank)
+    rois = torch.as_tensor(rois_h).to(dev)
+    roi_fn = lambda: ops.roi_align_rotated_v1.roi_align(feat, rois, (7, 7), 0.25, 2)
+    out = roi_fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    total_ms = time_steps(torch, roi_fn, K, W, flush, sampler)
+    torch.cuda.synchronize()
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        dist.barrier()
+    ms_per_step = total_ms / K
+    n_rois = rois.shape[0]
+    value = n_rois * world / (ms_per_step * 1e-3)
+    alg_bytes = feat.numel() * 4 + rois.numel() * 4 + out.numel() * 4        # 169 918 464 B
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "roi_align_rotated (nchw_to_nhwc relayout + roi_align_nhwc gather, 2 launches)",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "peak_source": peaks["source"], "algorithmic_bytes": alg_bytes, "traffic": None}
+
+    # ---- e2e: host buffers, H2D + op + D2H inside the timed region ----------------------------
+    feat_h = feat.cpu().pin_memory()
+    rois_p = torch.as_tensor(rois_h).pin_memory()
+    out_h = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+    feat_d, rois_d = torch.empty_like(feat), torch.empty_like(rois)
+
+    def e2e_fn():
+        feat_d.copy_(feat_h, non_blocking=True)
+        rois_d.copy_(rois_p, non_blocking=True)
+        o = ops.roi_align_rotated_v1.roi_align(feat_d, rois_d, (7, 7), 0.25, 2)
+        out_h.copy_(o, non_blocking=True)
+
+    Ke = max(3, min(K, 20))
+    e2e_ms = time_steps(torch, e2e_fn, Ke, 3, flush)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": n_rois * world / (e2e_ms / Ke * 1e-3), "unit": "RoIs/s", "ms_per_step": e2e_ms / Ke, "steps": Ke,
+           "h2d_bytes_per_step": int(feat.numel() * 4 + rois.numel() * 4), "d2h_bytes_per_step": int(out.numel() * 4)}
+
+    line = {"metric": "rotated RoIs/s", "value": value, "unit": "RoIs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "roi_align_rotated_v1: 256-ch 256x256 FPN map, 2048 RoIs, 7x7 output, sampling_ratio 2, "
+                                   "spatial_scale 0.25 (BASELINE configs[1]); one tile per GPU",
+                       "rois_per_gpu": n_rois, "l2": "256 MiB memset between timed steps (outside the events)",
+                       "timing": "CUDA events per step on the launch stream, max over ranks"},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": 2 * K, "roofline": roofline}
+
+    extra = {}
+    if not args.no_extra:
+        extra = run_extra(torch, dist if world > 1 else None, ops, jdist, dev, rank, world, peaks, flush)
+    line["extra"] = extra
+    if rank == 0 and world == 1 and not args.no_extra:
+        line["cpu_baseline"] = cpu_baseline_roi(feat.cpu().numpy(), rois_h)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_extra(torch, dist, ops, jdist, dev, rank, world, peaks, flush):
+    """The other hot-path ops at their BASELINE configs, each with its roofline line."""
+    from _inputs import clustered_boxes, dota_boxes, s2anet_anchors, tie_free_scores
+    from jdet_b200.models.roi_heads.s2anet_head import AlignConv
+    rng = np.random.default_rng(100 + rank)
+    cu = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
+    ex = {}
+
+    def agg(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # cfg3: nms_rotated, 100k proposals x 15 classes, thr 0.1 (+ all-gather of padded detections at N > 1)
+    n = 100000
+    d = np.concatenate([clustered_boxes(rng, n // 2, 50), dota_boxes(rng, n - n // 2)])
+    s, l = tie_free_scores(rng, n), rng.integers(0, 15, n)
+    td, ts, tl = cu(d), cu(s), cu(l, torch.int64)
+
+    def nms_fn():
+        keep = ops.nms_rotated.ml_nms_rotated(td, ts, tl, 0.1)
+        if dist is not None:
+            jdist.all_gather_detections(td, ts, tl, keep, max_per_img=2000)
+        return keep
+
+    kept = nms_fn()
+    K = 10
+    ms = agg(time_steps(torch, nms_fn, K, 3, flush)) / K
+    alg = n * (24 + 4 + 4 + 1)
+    ex["nms_rotated"] = {"metric": "rNMS boxes/s", "value": n * world / (ms * 1e-3), "unit": "boxes/s", "ms_per_step": ms,
+                         "steps": K, "config": {"workload": "ml_nms_rotated: 100k proposals (50% clustered) x 15 classes, IoU thr 0.1 "
+                                                            "(BASELINE configs[2])", "kept": int(kept.numel()),
+                                                "collective": "all_gather of 2000x7 padded detections per rank" if dist else "none"},
+                         "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                      "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg,
+                                      "note": "latency/ALU-bound by construction (sequential greedy dependency); bytes are 3.3 MB"}}
+
+    # box_iou_rotated 16k x 16k (1 GiB of IoUs) and cfg1 1k x 1k
+    for nn, K in ((16384, 10), (1000, 50)):
+        b1, b2 = cu(dota_boxes(rng, nn)), cu(dota_boxes(rng, nn))
+        fn = lambda: ops.box_iou_rotated(b1, b2)
+        fn()
+        ms = agg(time_steps(torch, fn, K, 3, flush)) / K
+        alg = 4 * nn * nn + 20 * 2 * nn
+        ex["box_iou_rotated_%dk" % (nn // 1000)] = {
+            "metric": "pairs/s", "value": nn * nn * world / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "steps": K,
+            "config": {"workload": "box_iou_rotated %dx%d DOTA-shaped OBBs" % (nn, nn)},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg}}
+        del b1, b2
+
+    # cfg4: S2ANet-R50-FPN shapes, bs 8: feature_refine + AlignConv over the 5 levels
+    levels = [(128, 8), (64, 16), (32, 32), (16, 64), (8, 128)]
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    xs = [torch.randn((8, 256, hw, hw), device=dev, generator=g) for hw, _ in levels]
+    an = [cu(s2anet_anchors(rng, 8, hw, hw, st)) for hw, st in levels]
+    bx = [a[..., [1, 0, 2, 3, 4]].contiguous() for a in an]
+    for points in (1, 5):
+        fn = lambda: [ops.fr.feature_refine(x, b, 1.0 / st, points) for x, b, (_, st) in zip(xs, bx, levels)]
+        fn()
+        K = 10
+        ms = agg(time_steps(torch, fn, K, 3, flush)) / K
+        alg = sum(2 * x.numel() * 4 + b.numel() * 4 for x, b in zip(xs, bx))
+        ex["feature_refine_p%d" % points] = {
+            "metric": "positions/s", "value": sum(x.shape[0] * x.shape[2] * x.shape[3] for x in xs) * world / (ms * 1e-3),
+            "unit": "positions/s", "ms_per_step": ms, "steps": K,
+            "config": {"workload": "feature_refine points=%d, bs 8 x 256 ch x {128,64,32,16,8}^2 (BASELINE configs[3])" % points},
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg}}
+    ac = AlignConv(256, 256, 3).to(dev)
+    fn = lambda: [ac(x, a, st) for x, a, (_, st) in zip(xs, an, levels)]
+    fn()
+    K = 5
+    ms = agg(time_steps(torch, fn, K, 3, flush)) / K
+    flops = 2.0 * 256 * 2304 * sum(x.shape[0] * x.shape[2] * x.shape[3] for x in xs)
+    ex["align_conv"] = {"metric": "positions/s", "value": sum(x.shape[0] * x.shape[2] * x.shape[3] for x in xs) * world / (ms * 1e-3),
+                        "unit": "positions/s", "ms_per_step": ms, "steps": K,
+                        "config": {"workload": "AlignConv 256->256 3x3, bs 8 x {128,64,32,16,8}^2 (BASELINE configs[3])"},
+                        "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"],
+                                     "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "flops": flops,
+                                     "note": "peak is the measured bf16 cuBLAS figure; the kernel computes fp32-class results"}}
+    return ex
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_roi(feat_np, rois_np, budget_s=12.0):
+    """Oracle port of ROIAlignRotated_v1 on the host cores (the reference has no CPU path for this op)."""
+    import oracle
+    sample = 256
+    t0 = time.perf_counter()
+    oracle.roi_align_rotated(feat_np, rois_np[:sample], (7, 7), 0.25, 2, 1)
+    dt = time.perf_counter() - t0
+    reps, tot = 0, 0.0
+    while tot < budget_s and reps < 20:
+        t0 = time.perf_counter()
+        oracle.roi_align_rotated(feat_np, rois_np[:sample], (7, 7), 0.25, 2, 1)
+        tot += time.perf_counter() - t0
+        reps += 1
+    per = tot / max(reps, 1) if reps else dt
+    out = {"value": sample / per, "unit": "RoIs/s", "cores": oracle.max_threads(), "kind": "port",
+           "sample": "%d of the 2048 cfg2 RoIs per repetition, %d repetitions, oracle/oracle.cpp orc_roi_align_rotated (OpenMP)" % (sample, reps)}
+    # the two ops that DO have a reference CPU path, timed from the reference's own source when it travelled
+    try:
+        import ctypes
+        from _inputs import clustered_boxes, dota_boxes, tie_free_scores
+        RC = oracle.ref_cpu()
+        rng = np.random.default_rng(0)
+        fp = ctypes.POINTER(ctypes.c_float)
+        if RC is not None:
+            b1, b2 = dota_boxes(rng, 1000), dota_boxes(rng, 1000)
+            o = np.zeros((1000, 1000), np.float32)
+            t0 = time.perf_counter()
+            RC.ref_box_iou_rotated_cpu(b1.ctypes.data_as(fp), 1000, b2.ctypes.data_as(fp), 1000, o.ctypes.data_as(fp))
+            dt = time.perf_counter() - t0
+            out["box_iou_rotated_1k"] = {"value": 1e6 / dt, "unit": "pairs/s", "cores": 1, "kind": "reference",
+                                         "sample": "cfg1 1000x1000, reference cpu_src (serial, as shipped)"}
+            n = 20000
+            d = np.concatenate([clustered_boxes(rng, n // 2, 50), dota_boxes(rng, n - n // 2)])
+            d6 = np.concatenate([d, rng.integers(0, 15, n)[:, None].astype(np.float32)], 1).astype(np.float32)
+            order = oracle.argsort_desc(tie_free_scores(rng, n))
+            keep, sup = np.zeros(n, np.bool_), np.zeros(n, np.uint8)
+            t0 = time.perf_counter()
+            RC.ref_nms_rotated_cpu(d6.ctypes.data_as(fp), n, 6, order.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                   ctypes.c_float(0.1), sup.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
+                                   keep.ctypes.data_as(ctypes.POINTER(ctypes.c_bool)))
+            dt = time.perf_counter() - t0
+            out["nms_rotated_20k"] = {"value": n / dt, "unit": "boxes/s", "cores": 1, "kind": "reference",
+                                      "sample": "20k of the cfg3 proposals x 15 classes (O(N^2) serial loop, as shipped)"}
+    except Exception as e:  # the baseline is a report, never a reason to fail the bench
+        out["note"] = "reference CPU legs skipped: %r" % (e,)
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the headline path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import oracle
+    rng = np.random.default_rng(1234)
+    feat = rng.standard_normal((1, 256, 256, 256)).astype(np.float32)
+    rois = make_cfg2(0)
+    sample = 256
+    K, W = args.steps, args.warmup
+    K = min(K, 40)
+    for _ in range(min(W, 3)):
+        oracle.roi_align_rotated(feat, rois[:sample], (7, 7), 0.25, 2, 1)
+    t0 = time.perf_counter()
+    for k in range(K):
+        lo = (k * sample) % 2048
+        oracle.roi_align_rotated(feat, rois[lo:lo + sample], (7, 7), 0.25, 2, 1)
+    dt = time.perf_counter() - t0
+    v = sample * K / dt
+    cores = oracle.max_threads()
+    line = {"impl": "reference", "metric": "rotated RoIs/s", "value": v, "unit": "RoIs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "roi_align_rotated_v1: 256-ch 256x256 FPN map, 2048 RoIs, 7x7 output, sampling_ratio 2, "
+                                   "spatial_scale 0.25 (BASELINE configs[1]); each step = %d of the 2048 RoIs" % sample},
+            "cpu_baseline": {"value": v, "unit": "RoIs/s", "cores": cores, "kind": "port",
+                             "sample": "%d RoIs per step x %d steps; the reference has no CPU path for roi_align_rotated "
+                                       "(CUDA-only), so this is oracle/oracle.cpp (OpenMP over RoIs)" % (sample, K)},
+            "e2e": {"value": v, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="headline op only (used under ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -217,7 +217,7 @@ def _rois(rng, R, B, extent, lo=8, hi=256):
     dict(B=2, C=64, H=40, W=56, R=300, out=(7, 7), sr=2, scale=0.25),      # staged (channel-last) path
     dict(B=1, C=128, H=32, W=32, R=200, out=(5, 3), sr=3, scale=0.125),    # staged, non-square bins
     dict(B=2, C=24, H=40, W=56, R=100, out=(7, 7), sr=2, scale=0.25),      # direct path (C % 64 != 0)
-    dict(B=2, C=64, H=64, W=64, R=3, out=(7, 7), sr=2, scale=0.0625),      # direct path (few RoIs)
+    dict(B=2, C=64, H=64, W=64, R=8, out=(7, 7), sr=2, scale=0.0625),      # direct path (few RoIs)
     dict(B=1, C=16, H=48, W=48, R=40, out=(7, 7), sr=0, scale=0.25),       # adaptive grid (sampling_ratio 0)
 ])
 def test_roi_align_vs_oracle(version, cfg):
