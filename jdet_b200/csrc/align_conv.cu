@@ -1,19 +1,26 @@
 // align_conv.cu — AlignConv.execute as one C-ABI call (s2anet_head.py:715-723).
 //
-// v1 composition: AlignConv offset field (deform_conv.cu) -> generic deformable implicit GEMM
-// (deform_conv.cu) with fused ReLU.  The tcgen05 fused kernel replaces this body when the shape
-// qualifies (align_conv_tc.cu).
+// Shapes that qualify (C % 32 == 0, Co % 32 == 0, Co <= 256 — every S2ANet level) run the fused
+// tcgen05 kernel in align_conv_tc.cu.  Anything else composes the AlignConv offset field with the
+// generic deformable implicit GEMM of deform_conv.cu (fused ReLU).
 #include "common.cuh"
 
 extern "C" int jdet_align_conv_offset(const float*, int, int, int, float, int, float*, void*);
 extern "C" int jdet_deform_conv_forward(const float*, const float*, const float*, int, int, int, int, int, int, int,
                                         int, int, int, int, int, int, int, int, int, float*, void*);
 
+namespace jdet {
+bool align_conv_tc_supported(int C, int Co);
+size_t align_conv_tc_workspace_bytes(int N, int C, int H, int W, int Co);
+int align_conv_tc_launch(const float* x, const float* anchors, const float* weight, int N, int C, int H, int W, int Co,
+                         float stride, float* out, void* workspace, cudaStream_t st);
+}  // namespace jdet
+
 JDET_API const char* jdet_version(void) { return "jdet_b200 0.1.0 sm_100a"; }
 
 JDET_API size_t jdet_align_conv_forward_workspace_bytes(int N, int C, int H, int W, int Co) {
-  (void)C; (void)Co;
-  if (N <= 0 || H <= 0 || W <= 0) return 256;
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Co <= 0) return 256;
+  if (jdet::align_conv_tc_supported(C, Co)) return jdet::align_conv_tc_workspace_bytes(N, C, H, W, Co);
   return jdet_align_up((size_t)N * 18 * H * W * sizeof(float), 256);
 }
 
@@ -24,6 +31,8 @@ JDET_API int jdet_align_conv_forward(const float* x, const float* anchors, const
   if (N == 0) return 0;
   if (!x || !anchors || !weight || !out) return JDET_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < jdet_align_conv_forward_workspace_bytes(N, C, H, W, Co)) return JDET_ERR_WORKSPACE;
+  if (jdet::align_conv_tc_supported(C, Co))
+    return jdet::align_conv_tc_launch(x, anchors, weight, N, C, H, W, Co, stride, out, workspace, (cudaStream_t)stream);
   float* offset = (float*)workspace;
   int e = jdet_align_conv_offset(anchors, N, H, W, stride, 3, offset, stream);
   if (e) return e;

@@ -1,0 +1,380 @@
+// align_conv_tc.cu — S2ANet AlignConv as ONE fused tcgen05 implicit GEMM for sm_100a.
+//
+// Replaces AlignConv.execute (/root/reference/python/jdet/models/roi_heads/s2anet_head.py:715-723):
+//   get_offset (:677-713, ~25 elementwise kernels per image) -> deformable_im2col
+//   (ops/dcn_v1.py:131-184, a 1.2 GB columns tensor at level 0) -> jt.matmul / cuBLAS SGEMM
+//   (ops/dcn_v1.py:446-447) -> ReLU.
+//
+// B200 design (no offsets tensor, no columns tensor):
+//   D[pixel, co] = sum_k A[pixel, k] * Wt[co, k],  k = tap*C + c  (tap-major K; weights re-packed once)
+//   M tile = 128 output pixels, N = Co (<= 256, the whole output-channel extent), K block = 32.
+//   A operand  : produced in-kernel.  4 producer warps derive the 9 sampling points of each pixel
+//                straight from its refined anchor (same fp32 op order as get_offset + im2col), gather
+//                the 4 bilinear corners from a channel-last copy of x with 16-B loads (8 lanes = 32
+//                channels = one 128-B row), interpolate in fp32, split each value into two TF32 terms
+//                (hi = top 19 bits, lo = exact remainder) and write both into shared memory directly in
+//                the UMMA canonical K-major SWIZZLE_128B layout.
+//   B operand  : weights pre-split into hi/lo and pre-swizzled in global memory, one contiguous
+//                Co x 128 B block per K block -> a single cp.async.bulk (TMA engine, UBLKCP) per term.
+//   MMA        : one elected thread issues tcgen05.mma.kind::tf32 128 x Co x 8; 3 products per K step
+//                (hi*hi + hi*lo + lo*hi  == "3xTF32", ~2^-21 relative error, fp32-class like the
+//                reference's SGEMM); accumulators live in TMEM, double-buffered (2 x Co columns) so the
+//                epilogue of tile i overlaps the main loop of tile i+1.
+//   Epilogue   : 4 warps, tcgen05.ld 32x32b -> ReLU -> NCHW stores (a warp writes 128 contiguous bytes
+//                per output channel).
+//   Persistent : grid = min(#tiles, 148); warp roles: 0-3 epilogue, 4-7 A producers, 8 MMA + TMEM
+//                alloc, 9 B loader.  Barriers are mbarriers (full/empty per smem stage, full/empty per
+//                TMEM accumulator stage).
+//
+// Layout in HBM: x (N,C,H,W) fp32 -> channel-last scratch (N,H,W,C); anchors (N,H,W,5); weight
+// (Co,C,3,3) -> scratch [9*C/32][Co][32] hi and lo (swizzled); out (N,Co,H,W).
+#include "common.cuh"
+
+namespace jdet {
+
+void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cudaStream_t st);   // relayout.cu
+
+namespace tc {
+
+constexpr int kThreads = 320;
+constexpr int kStages = 2;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;                 // fp32 elements = one 128-B swizzle row
+constexpr int kABytes = kBlockM * 128;      // 16 KB per term
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+struct Params {
+  const float* x_nhwc;      // (N, H, W, C)
+  const float* anchors;     // (N, H, W, 5)
+  const float* b_hi;        // [K/32][Co][32] swizzled
+  const float* b_lo;
+  float* out;               // (N, Co, H, W)
+  int N, C, H, W, Co;
+  float stride;
+  int num_tiles;
+};
+
+// weight (Co, C, 3, 3) -> hi/lo [kb][co][32] with kb = tap*(C/32) + c/32, 16-B chunks XOR-swizzled by (co & 7)
+__global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, int Co, int C, float* __restrict__ hi,
+                                                           float* __restrict__ lo) {
+  const long long total = (long long)Co * C * 9;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int t = (int)(i % 9);
+  const int c = (int)((i / 9) % C);
+  const int co = (int)(i / (9LL * C));
+  const float v = w[i];
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  const float l = v - h;                                      // exact
+  const int kb = t * (C / 32) + c / 32, e = c % 32;
+  const int chunk = (e >> 2) ^ (co & 7);
+  const size_t dst = ((size_t)kb * Co + co) * 32 + chunk * 4 + (e & 3);
+  hi[dst] = h;
+  lo[dst] = l;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.Co * 128;
+  const int stage_bytes = 2 * kABytes + 2 * b_bytes;
+  auto a_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
+  auto a_lo = [&](int s) { return smem + (size_t)s * stage_bytes + kABytes; };
+  auto b_hi = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * kABytes; };
+  auto b_lo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * kABytes + b_bytes; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* empty = bars + kStages;      // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;  // [2]
+  uint64_t* tempty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = p.H * p.W;
+  const long long P = (long long)p.N * HW;
+  const int cblocks = p.C / 32;
+  const int num_kb = 9 * cblocks;
+
+  if (warp == 9 && lane == 0) {
+    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // =============================== A producers ==============================================
+    const int pw = warp - 4, sp = lane >> 3, q = lane & 7;
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      // per-pixel anchor geometry (s2anet_head.py:689-698), 8 pixels per lane
+      float gx[8], gy[8], gdw[8], gdh[8], gc[8], gs[8], fh[8], fw[8];
+      long long pbase[8];          // n * HW (pixel index of the image origin), -1 => row beyond the tensor
+#pragma unroll
+      for (int it = 0; it < 8; it++) {
+        const int r = pw * 32 + it * 4 + sp;
+        const long long pix = (long long)tile * kBlockM + r;
+        if (pix < P) {
+          const int n = (int)(pix / HW), hw = (int)(pix - (long long)n * HW);
+          const int h = hw / p.W, w = hw - h * p.W;
+          const float* a = p.anchors + pix * 5;
+          gx[it] = __fdiv_rn(__ldg(a + 0), p.stride);
+          gy[it] = __fdiv_rn(__ldg(a + 1), p.stride);
+          gdw[it] = __fdiv_rn(__fdiv_rn(__ldg(a + 2), p.stride), 3.f);
+          gdh[it] = __fdiv_rn(__fdiv_rn(__ldg(a + 3), p.stride), 3.f);
+          const float ang = __ldg(a + 4);
+          gc[it] = cosf(ang);
+          gs[it] = sinf(ang);
+          fh[it] = (float)h;
+          fw[it] = (float)w;
+          pbase[it] = (long long)n * HW;
+        } else {
+          gx[it] = gy[it] = gdw[it] = gdh[it] = gc[it] = gs[it] = fh[it] = fw[it] = 0.f;
+          pbase[it] = -1;
+        }
+      }
+      for (int t = 0; t < 9; t++) {
+        // tap geometry once per tap, reused by the C/32 channel blocks
+        int o00[8], o01[8], o10[8], o11[8];
+        float w1[8], w2[8], w3[8], w4[8];
+        const float xx = (float)(t % 3 - 1), yy = (float)(t / 3 - 1);
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+          const float x = __fmul_rn(gdw[it], xx), y = __fmul_rn(gdh[it], yy);
+          const float xr = __fsub_rn(__fmul_rn(gc[it], x), __fmul_rn(gs[it], y));
+          const float yr = __fadd_rn(__fmul_rn(gs[it], x), __fmul_rn(gc[it], y));
+          const float xa = __fadd_rn(xr, gx[it]), ya = __fadd_rn(yr, gy[it]);
+          const float cw = __fadd_rn(fw[it], xx), chh = __fadd_rn(fh[it], yy);     // regular conv location
+          const float w_im = __fadd_rn(cw, __fsub_rn(xa, cw));                     // dcn_v1.py:168-169
+          const float h_im = __fadd_rn(chh, __fsub_rn(ya, chh));
+          o00[it] = o01[it] = o10[it] = o11[it] = -1;
+          w1[it] = w2[it] = w3[it] = w4[it] = 0.f;
+          if (pbase[it] >= 0 && h_im > -1.f && w_im > -1.f && h_im < (float)p.H && w_im < (float)p.W) {
+            const int hl = (int)floorf(h_im), wl = (int)floorf(w_im);
+            const int hh = hl + 1, wh = wl + 1;
+            const float lh = h_im - (float)hl, lw = w_im - (float)wl;
+            const float uh = 1.f - lh, uw = 1.f - lw;
+            w1[it] = uh * uw; w2[it] = uh * lw; w3[it] = lh * uw; w4[it] = lh * lw;
+            if (hl >= 0 && wl >= 0) o00[it] = hl * p.W + wl;
+            if (hl >= 0 && wh <= p.W - 1) o01[it] = hl * p.W + wh;
+            if (hh <= p.H - 1 && wl >= 0) o10[it] = hh * p.W + wl;
+            if (hh <= p.H - 1 && wh <= p.W - 1) o11[it] = hh * p.W + wh;
+          }
+        }
+        for (int cb = 0; cb < cblocks; cb++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* ah = a_hi(stage);
+          unsigned char* al = a_lo(stage);
+          float4 v[8];
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 a = z, b = z, c = z, d = z;
+            if (pbase[it] >= 0) {
+              const float* base = p.x_nhwc + (size_t)cb * 32 + q * 4;
+              const size_t pb = (size_t)pbase[it];
+              if (o00[it] >= 0) a = __ldg(reinterpret_cast<const float4*>(base + (pb + o00[it]) * p.C));
+              if (o01[it] >= 0) b = __ldg(reinterpret_cast<const float4*>(base + (pb + o01[it]) * p.C));
+              if (o10[it] >= 0) c = __ldg(reinterpret_cast<const float4*>(base + (pb + o10[it]) * p.C));
+              if (o11[it] >= 0) d = __ldg(reinterpret_cast<const float4*>(base + (pb + o11[it]) * p.C));
+            }
+            v[it].x = w1[it] * a.x + w2[it] * b.x + w3[it] * c.x + w4[it] * d.x;
+            v[it].y = w1[it] * a.y + w2[it] * b.y + w3[it] * c.y + w4[it] * d.y;
+            v[it].z = w1[it] * a.z + w2[it] * b.z + w3[it] * c.z + w4[it] * d.z;
+            v[it].w = w1[it] * a.w + w2[it] * b.w + w3[it] * c.w + w4[it] * d.w;
+          }
+#pragma unroll
+          for (int it = 0; it < 8; it++) {
+            const int r = pw * 32 + it * 4 + sp;
+            const uint32_t off = (uint32_t)r * 128u + (uint32_t)((q ^ (r & 7)) << 4);
+            float4 h4, l4;
+            h4.x = __uint_as_float(__float_as_uint(v[it].x) & 0xffffe000u); l4.x = v[it].x - h4.x;
+            h4.y = __uint_as_float(__float_as_uint(v[it].y) & 0xffffe000u); l4.y = v[it].y - h4.y;
+            h4.z = __uint_as_float(__float_as_uint(v[it].z) & 0xffffe000u); l4.z = v[it].z - h4.z;
+            h4.w = __uint_as_float(__float_as_uint(v[it].w) & 0xffffe000u); l4.w = v[it].w - h4.w;
+            *reinterpret_cast<float4*>(ah + off) = h4;
+            *reinterpret_cast<float4*>(al + off) = l4;
+          }
+          fence_proxy_async();             // generic-proxy stores -> visible to the tensor-core (async) proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =============================== B loader ==================================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], 2u * (uint32_t)b_bytes);
+          bulk_g2s(b_hi(stage), p.b_hi + (size_t)kb * p.Co * 32, (uint32_t)b_bytes, &full[stage]);
+          bulk_g2s(b_lo(stage), p.b_lo + (size_t)kb * p.Co * 32, (uint32_t)b_bytes, &full[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer =================================================
+    // instruction descriptor: D=F32, A=B=TF32, K-major both, N = Co, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co;
+      for (int kb = 0; kb < num_kb; kb++) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t ah = make_desc(smem_u32(a_hi(stage))), al = make_desc(smem_u32(a_lo(stage)));
+          const uint64_t bh = make_desc(smem_u32(b_hi(stage))), bl = make_desc(smem_u32(b_lo(stage)));
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 8; kk++) {
+            const uint64_t adv = (uint64_t)(kk * 2);     // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle row
+            tc_mma_tf32(d_tmem, al + adv, bh + adv, idesc, (kb | kk) ? 1u : 0u);   // small terms first
+            tc_mma_tf32(d_tmem, ah + adv, bl + adv, idesc, 1u);
+            tc_mma_tf32(d_tmem, ah + adv, bh + adv, idesc, 1u);
+          }
+          tc_commit(&empty[stage]);                       // frees the smem stage when these MMAs retire
+          if (kb == num_kb - 1) tc_commit(&tfull[acc]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // =============================== epilogue (warps 0-3) ======================================
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int r = warp * 32 + lane;
+      const long long pix = (long long)tile * kBlockM + r;
+      const bool ok = pix < P;
+      const int n = ok ? (int)(pix / HW) : 0;
+      const int hw = ok ? (int)(pix - (long long)n * HW) : 0;
+      float* obase = p.out + (size_t)n * p.Co * HW + hw;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)p.Co;
+      for (int c0 = 0; c0 < p.Co; c0 += 32) {
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) st_stream(obase + (size_t)(c0 + j) * HW, fmaxf(__uint_as_float(v[j]), 0.f));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+}  // namespace tc
+
+bool align_conv_tc_supported(int C, int Co) { return C % 32 == 0 && Co % 32 == 0 && Co >= 32 && Co <= 256; }
+
+size_t align_conv_tc_workspace_bytes(int N, int C, int H, int W, int Co) {
+  return jdet_align_up((size_t)N * C * H * W * 4, 1024) + 2 * jdet_align_up((size_t)Co * C * 9 * 4, 1024);
+}
+
+int align_conv_tc_launch(const float* x, const float* anchors, const float* weight, int N, int C, int H, int W, int Co,
+                         float stride, float* out, void* workspace, cudaStream_t st) {
+  using namespace tc;
+  float* x_nhwc = (float*)workspace;
+  float* b_hi = (float*)((char*)workspace + jdet_align_up((size_t)N * C * H * W * 4, 1024));
+  float* b_lo = (float*)((char*)b_hi + jdet_align_up((size_t)Co * C * 9 * 4, 1024));
+  launch_nchw_to_nhwc(x, x_nhwc, N, C, H * W, st);
+  const long long wt = (long long)Co * C * 9;
+  weight_prep_kernel<<<(int)((wt + 255) / 256), 256, 0, st>>>(weight, Co, C, b_hi, b_lo);
+  Params p{x_nhwc, anchors, b_hi, b_lo, out, N, C, H, W, Co, stride, 0};
+  const long long P = (long long)N * H * W;
+  p.num_tiles = (int)((P + kBlockM - 1) / kBlockM);
+  const size_t smem = 1024 + (size_t)kStages * (2 * kABytes + 2 * (size_t)Co * 128) + 256;
+  cudaError_t e = cudaFuncSetAttribute(align_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  align_conv_tc_kernel<<<grid, kThreads, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace jdet

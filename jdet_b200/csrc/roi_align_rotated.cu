@@ -106,28 +106,7 @@ __device__ __forceinline__ SampleTap make_tap(const RoiGeom& g, int ph, int pw, 
   return t;
 }
 
-// ---- NCHW -> NHWC re-layout --------------------------------------------------------------------
-// in: (B, C, HW)   out: (B, HW, C).  32x32 tiles through padded smem; both sides 128-B coalesced.
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                            int C, int HW) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  const float* src = in + (size_t)b * C * HW;
-  float* dst = out + (size_t)b * C * HW;
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int c = c0 + ty + 8 * k, p = p0 + tx;
-    if (c < C && p < HW) tile[ty + 8 * k][tx] = __ldg(src + (size_t)c * HW + p);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int p = p0 + ty + 8 * k, c = c0 + tx;
-    if (c < C && p < HW) dst[(size_t)p * C + c] = tile[tx][ty + 8 * k];
-  }
-}
+void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cudaStream_t st);   // relayout.cu
 
 // ---- staged gather kernel ----------------------------------------------------------------------
 // grid = (R, C/64 slabs); 256 threads.  Requires C % 64 == 0 and PH*PW*gh*gw <= kMaxSamples
@@ -270,8 +249,7 @@ JDET_API int jdet_roi_align_rotated(int version, const float* input, int B, int 
     const size_t need = jdet_align_up((size_t)B * C * H * W * sizeof(float), 256);
     if (!workspace || workspace_bytes < need) return JDET_ERR_WORKSPACE;
     float* nhwc = (float*)workspace;
-    dim3 tg(jdet_ceil_div(H * W, 32), jdet_ceil_div(C, 32), B);
-    nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(input, nhwc, C, H * W);
+    launch_nchw_to_nhwc(input, nhwc, B, C, H * W, st);
     const size_t smem = (size_t)nbins * sampling_ratio * sampling_ratio * sizeof(SampleTap) + (size_t)64 * nbins * 4;
     dim3 grid(R, C / 64);
     if (version == 1) {

@@ -326,7 +326,8 @@ def test_deform_conv_groups_match_per_group_oracle():
         assert np.abs(got[:, gi * 6:(gi + 1) * 6] - want).max() <= TOL
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 16, 16, 64, 8), (1, 256, 32, 32, 256, 16), (2, 32, 9, 7, 48, 32)])
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16, 64, 8), (1, 256, 32, 32, 256, 16), (2, 32, 9, 7, 48, 32),
+                                   (3, 64, 13, 11, 96, 8), (8, 128, 64, 64, 256, 16), (5, 32, 8, 8, 32, 128)])
 def test_align_conv_vs_oracle(shape):
     N, C, H, W, Co, stride = shape
     rng = np.random.default_rng(C + H)
