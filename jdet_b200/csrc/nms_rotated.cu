@@ -27,8 +27,8 @@
 
 namespace jdet {
 
-constexpr int kCH = 16;            // column blocks per work item
-constexpr int kMaskThreads = 128;
+constexpr int kCH = 8;             // column blocks per work item
+constexpr int kMaskThreads = 256;
 constexpr int kQCap = 8192;        // survivor queue entries per CTA
 
 struct NmsWs {
@@ -123,11 +123,14 @@ __global__ void seg_count_kernel(const int* __restrict__ seg_start, const int* _
   seg_items[s] = items; seg_tiles[s] = tiles;
 }
 
-__device__ __forceinline__ long long tri_index(long long W, long long rb, long long cb) {
-  return rb * W - rb * (rb - 1) / 2 + (cb - rb);
-}
+// Mask layout: per segment, upper-triangular 64x64 tiles in COLUMN-block-major order, so the scan
+// warp that owns column block cb streams tiles (0..cb, cb) from one contiguous run.
+__device__ __forceinline__ long long tri_index(long long rb, long long cb) { return cb * (cb + 1) / 2 + rb; }
 
 // ---- mask kernel ---------------------------------------------------------------------------------
+// One work item = (segment, row block rb, chunk of up to kCH column blocks).  256 threads.
+//   phase 1  thread <-> 2 columns (registers), loop over the 64 rows (broadcast LDS.128): circle test
+//   phase 2  SAT on compacted survivors          phase 3  exact IoU, strict "> thr", bits via smem atomics
 // label_in_pair != 0 (thr < 0 corner): single segment, no quick rejects, label mismatch => IoU 0.
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     const BoxRec* __restrict__ rec, const int* __restrict__ seg_start, const int* __restrict__ item_base,
@@ -135,10 +138,11 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     int label_in_pair, int* __restrict__ counter, unsigned long long* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   BoxRec* s_row = reinterpret_cast<BoxRec*>(s_dyn);                       //  2 KB
-  BoxRec* s_col = s_row + 64;                                             // 32 KB
-  unsigned* s_bits = reinterpret_cast<unsigned*>(s_col + kCH * 64);       //  8 KB: tile words as (lo, hi)
-  unsigned short* s_q1 = reinterpret_cast<unsigned short*>(s_bits + kCH * 64 * 2);   // 16 KB
-  unsigned short* s_q2 = s_q1 + kQCap;                                    // 16 KB
+  BoxRec* s_col = s_row + 64;                                             // 16 KB
+  float4* s_rowq = reinterpret_cast<float4*>(s_col + kCH * 64);           //  1 KB  (x, y, qr, -)
+  unsigned* s_bits = reinterpret_cast<unsigned*>(s_rowq + 64);            //  4 KB: tile words as (lo, hi)
+  unsigned short* s_q1 = reinterpret_cast<unsigned short*>(s_bits + kCH * 64 * 2);   // 2 x kQCap entries
+  unsigned short* s_q2 = s_q1 + kQCap;
   __shared__ int s_cnt1, s_cnt2, s_item;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -151,7 +155,6 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     __syncthreads();
     const int item = s_item;
     if (item >= total) break;
-    // segment by binary search on item_base[0..nseg]
     int lo = 0, hi = nseg;                               // item_base[lo] <= item < item_base[hi]
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (item_base[mid] <= item) lo = mid; else hi = mid; }
     const int seg = lo;
@@ -165,116 +168,141 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     const int chunk = (int)(local - (FW - items_prefix(W - rb)));
     const int cb0 = rb + chunk * kCH;
     const int ncb = min(kCH, W - cb0);
+    const int ncols = ncb * 64;
 
-    // stage boxes
+    const BoxRec dead{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, -INFINITY, 0.f};
     if (tid < 64) {
       const int p = rb * 64 + tid;
-      BoxRec r;
-      if (p < cnt) r = rec[s0 + p];
-      else { r.x = r.y = r.w = r.h = r.c2 = r.s2 = 0.f; r.qr = -INFINITY; r.tag = 0.f; }
+      const BoxRec r = (p < cnt) ? rec[s0 + p] : dead;
       s_row[tid] = r;
+      s_rowq[tid] = make_float4(r.x, r.y, r.qr, 0.f);
     }
-    for (int k = tid; k < ncb * 64; k += kMaskThreads) {
-      const int p = cb0 * 64 + k;
-      BoxRec r;
-      if (p < cnt) r = rec[s0 + p];
-      else { r.x = r.y = r.w = r.h = r.c2 = r.s2 = 0.f; r.qr = -INFINITY; r.tag = 0.f; }
-      s_col[k] = r;
+    // this thread's two columns stay in registers for phase 1
+    float cx[2], cy[2], cq[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int c = tid + j * kMaskThreads;
+      BoxRec r = dead;
+      if (c < ncols) {
+        const int p = cb0 * 64 + c;
+        if (p < cnt) r = rec[s0 + p];
+        s_col[c] = r;
+      }
+      cx[j] = r.x; cy[j] = r.y; cq[j] = r.qr;
     }
     for (int k = tid; k < ncb * 128; k += kMaskThreads) s_bits[k] = 0u;
     if (tid == 0) { s_cnt1 = 0; s_cnt2 = 0; }
     __syncthreads();
 
-    const int row = tid & 63, half = tid >> 6;           // thread: one row x 32 columns of a tile
-    const float rx = s_row[row].x, ry = s_row[row].y, rr = s_row[row].qr;
-    const int grow = rb * 64 + row;
-
-    for (int t = 0; t < ncb; t++) {
-      // phase 1 for tile t
-      unsigned surv = 0;
-      const int cbase = t * 64 + half * 32;
-      const int gcol0 = (cb0 + t) * 64 + half * 32;
+    // ---- phase 1 ---------------------------------------------------------------------------------
+    unsigned long long m[2] = {0ull, 0ull};               // bit r: (row r, my column j) survives
+    if (!label_in_pair) {
 #pragma unroll 8
-      for (int c = 0; c < 32; c++) {
-        const BoxRec& B = s_col[cbase + c];
-        bool s;
-        if (label_in_pair) s = (gcol0 + c < cnt) && (grow < cnt);
-        else s = !circle_disjoint(rx, ry, rr, B.x, B.y, B.qr);
-        s = s && (gcol0 + c > grow);                    // strictly upper triangle
-        surv |= (s ? 1u : 0u) << c;
+      for (int r = 0; r < 64; r++) {
+        const float4 rq = s_rowq[r];
+        m[0] |= (unsigned long long)(circle_disjoint(rq.x, rq.y, rq.z, cx[0], cy[0], cq[0]) ? 0u : 1u) << r;
+        m[1] |= (unsigned long long)(circle_disjoint(rq.x, rq.y, rq.z, cx[1], cy[1], cq[1]) ? 0u : 1u) << r;
       }
-      {
-        const int c = __popc(surv);
-        int incl = c;
+    } else {
+      const int nrow = min(64, cnt - rb * 64);
+      const unsigned long long rows = nrow >= 64 ? ~0ull : ((1ull << nrow) - 1ull);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-        const int tot = __shfl_sync(0xffffffffu, incl, 31);
-        int base = 0;
-        if (lane == 31 && tot > 0) base = atomicAdd(&s_cnt1, tot);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        int pos = base + incl - c;
-        while (surv) {
-          const int b = __ffs(surv) - 1; surv &= surv - 1;
-          s_q1[pos++] = (unsigned short)((t << 12) | (row << 6) | (half * 32 + b));
+      for (int j = 0; j < 2; j++) {
+        const int c = tid + j * kMaskThreads;
+        if (c < ncols && cb0 * 64 + c < cnt) m[j] = rows;
+      }
+    }
+    // strictly upper triangle: in the diagonal tile (cb == rb) column c only meets rows r < c
+    if (cb0 == rb) {
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int c = tid + j * kMaskThreads;
+        if (c < 64) m[j] &= (c == 0) ? 0ull : ((1ull << c) - 1ull);
+      }
+    }
+    // Survivors -> queue.  Candidates per item are normally a few hundred; if they exceed kQCap the
+    // remainder stays in the per-thread masks and goes through another round of phases 2 and 3.
+    for (;;) {
+      const int want = __popcll(m[0]) + __popcll(m[1]);
+      int incl = want;                                   // warp inclusive scan, one atomic per warp
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      int base = 0;
+      if (lane == 31 && tot > 0) base = atomicAdd(&s_cnt1, tot);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      int pos = base + incl - want;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int c = tid + j * kMaskThreads;
+        while (m[j] && pos < kQCap) {
+          const int r = __ffsll((long long)m[j]) - 1;
+          m[j] &= m[j] - 1;
+          s_q1[pos++] = (unsigned short)(((c >> 6) << 12) | (r << 6) | (c & 63));
+        }
+      }
+      const int pending = __syncthreads_or((m[0] | m[1]) != 0ull);
+      const int c1 = min(s_cnt1, kQCap);
+      // ---- phase 2: SAT ----------------------------------------------------------------------------
+      for (int b0 = 0; b0 < c1; b0 += kMaskThreads) {
+        const int k = b0 + tid;
+        bool keep = false; unsigned short e = 0;
+        if (k < c1) {
+          e = s_q1[k];
+          keep = label_in_pair ? true : !sat_disjoint<0>(s_row[(e >> 6) & 63], s_col[(e >> 12) * 64 + (e & 63)]);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (bal) {
+          int wb = 0;
+          if (lane == 0) wb = atomicAdd(&s_cnt2, __popc(bal));
+          wb = __shfl_sync(0xffffffffu, wb, 0);
+          if (keep) s_q2[wb + __popc(bal & ((1u << lane) - 1u))] = e;
         }
       }
       __syncthreads();
-      const int c1 = s_cnt1;
-      __syncthreads();                                   // everyone has read c1 before it moves again
-      const bool flush = (t == ncb - 1) || (c1 + 4096 > kQCap);
-      if (flush) {
-        // phase 2: SAT
-        for (int base = 0; base < c1; base += kMaskThreads) {
-          const int k = base + tid;
-          bool keep = false; unsigned short e = 0;
-          if (k < c1) {
-            e = s_q1[k];
-            const BoxRec& A = s_row[(e >> 6) & 63];
-            const BoxRec& B = s_col[(e >> 12) * 64 + (e & 63)];
-            keep = label_in_pair ? true : !sat_disjoint<0>(A, B);
-          }
-          const unsigned bal = __ballot_sync(0xffffffffu, keep);
-          if (bal) {
-            int wb = 0;
-            if (lane == 0) wb = atomicAdd(&s_cnt2, __popc(bal));
-            wb = __shfl_sync(0xffffffffu, wb, 0);
-            if (keep) s_q2[wb + __popc(bal & ((1u << lane) - 1u))] = e;
-          }
-        }
-        __syncthreads();
-        // phase 3: exact IoU, strict > thr
-        const int c2 = s_cnt2;
-        for (int k = tid; k < c2; k += kMaskThreads) {
-          const unsigned short e = s_q2[k];
-          const int r = (e >> 6) & 63, tt = e >> 12, c = e & 63;
-          const BoxRec& A = s_row[r];
-          const BoxRec& B = s_col[tt * 64 + c];
-          float v;
-          if (label_in_pair && A.tag != B.tag) v = 0.f;   // nms_rotated.py:285-286
-          else v = iou_exact<0>(A, B);
-          if (v > thr) atomicOr(&s_bits[(tt * 64 + r) * 2 + (c >> 5)], 1u << (c & 31));
-        }
-        __syncthreads();
-        if (tid == 0) { s_cnt1 = 0; s_cnt2 = 0; }
-        __syncthreads();
+      // ---- phase 3: exact IoU, strict > thr ----------------------------------------------------------
+      const int c2 = s_cnt2;
+      for (int k = tid; k < c2; k += kMaskThreads) {
+        const unsigned short e = s_q2[k];
+        const int r = (e >> 6) & 63, tt = e >> 12, cc = e & 63;
+        const BoxRec& A = s_row[r];
+        const BoxRec& B = s_col[tt * 64 + cc];
+        float v;
+        if (label_in_pair && A.tag != B.tag) v = 0.f;   // nms_rotated.py:285-286
+        else v = iou_exact<0>(A, B);
+        if (v > thr) atomicOr(&s_bits[(tt * 64 + r) * 2 + (cc >> 5)], 1u << (cc & 31));
       }
+      __syncthreads();
+      if (!pending) break;
+      if (tid == 0) { s_cnt1 = 0; s_cnt2 = 0; }
+      __syncthreads();
     }
-    // write tiles (rb, cb0 .. cb0+ncb-1): contiguous in the triangular layout
-    unsigned long long* dst = mask + (tile_base[seg] + tri_index(W, rb, cb0)) * 64;
-    for (int k = tid; k < ncb * 64; k += kMaskThreads)
-      dst[k] = ((unsigned long long)s_bits[2 * k + 1] << 32) | s_bits[2 * k];
+    // tiles (rb, cb0 + t): column-block-major triangular layout
+    unsigned long long* mbase = mask + tile_base[seg] * 64;
+    for (int k = tid; k < ncb * 64; k += kMaskThreads) {
+      const int t = k >> 6, r = k & 63;
+      mbase[tri_index(rb, cb0 + t) * 64 + r] = ((unsigned long long)s_bits[2 * k + 1] << 32) | s_bits[2 * k];
+    }
   }
 }
 
 // ---- scan kernel ---------------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
+// One CTA per segment (persistent over segments), kScanWarps warps.  Warp w OWNS column blocks
+// cb = w, w + kScanWarps, ...: it ORs the rows kept in earlier blocks into its own running word
+// (a warp-uniform register — there is no shared remv[] array), resolves its diagonal tile with
+// ballots, writes the keep flags, and publishes kept(cb) + a progress counter through shared
+// memory.  Loads never depend on kept(), so each warp prefetches a batch of tiles and only the
+// masking waits; the serial chain per block is "apply tile (cb-1, cb) -> resolve diag -> publish".
+constexpr int kScanWarps = 16;
+constexpr int kScanThreads = kScanWarps * 32;
+constexpr int kScanBatch = 8;
 
 __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(
     const int* __restrict__ seg_start, const long long* __restrict__ tile_base, const int* __restrict__ scan,
     int n, const int* __restrict__ sorted_idx, const unsigned long long* __restrict__ mask,
     unsigned char* __restrict__ keep) {
-  extern __shared__ unsigned long long s_remv[];
-  __shared__ unsigned long long s_kept;
+  extern __shared__ unsigned long long s_kept[];       // [W]
+  __shared__ volatile int s_progress;                   // number of column blocks resolved so far
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nseg = scan[n - 1];
   for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
@@ -282,45 +310,62 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(
     const int W = (cnt + 63) >> 6;
     const unsigned long long* base = mask + tile_base[seg] * 64;
     __syncthreads();
-    for (int k = tid; k < W; k += kScanThreads) s_remv[k] = 0ull;
+    if (tid == 0) s_progress = 0;
     __syncthreads();
-    for (int rb = 0; rb < W; rb++) {
-      if (warp == 0) {
-        const unsigned long long* diag = base + tri_index(W, rb, rb) * 64;
-        const unsigned long long w0 = diag[lane], w1 = diag[lane + 32];
-        unsigned long long cur = s_remv[rb];
-        const unsigned nz0 = __ballot_sync(0xffffffffu, w0 != 0ull), nz1 = __ballot_sync(0xffffffffu, w1 != 0ull);
-        const unsigned long long nz = ((unsigned long long)nz1 << 32) | nz0;
-        unsigned long long done = 0ull;
-        for (;;) {
-          const unsigned long long cand = nz & ~cur & ~done;
-          if (!cand) break;
-          const int r = __ffsll((long long)cand) - 1;   // lowest kept row with a non-empty word
-          const unsigned long long wsel = (r < 32) ? w0 : w1;
-          const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)wsel, r & 31);
-          const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(wsel >> 32), r & 31);
-          cur |= ((unsigned long long)hi << 32) | lo;
-          done |= 1ull << r;
+    for (int cb = warp; cb < W; cb += kScanWarps) {
+      const unsigned long long* col = base + tri_index(0, cb) * 64;     // tiles (0..cb, cb), contiguous
+      unsigned acc_lo = 0u, acc_hi = 0u;
+      for (int rb0 = 0; rb0 < cb; rb0 += kScanBatch) {
+        const int nb = min(kScanBatch, cb - rb0);
+        unsigned long long w0[kScanBatch], w1[kScanBatch];
+#pragma unroll
+        for (int b = 0; b < kScanBatch; b++) {
+          if (b < nb) { w0[b] = col[(size_t)(rb0 + b) * 64 + lane]; w1[b] = col[(size_t)(rb0 + b) * 64 + lane + 32]; }
+          else { w0[b] = 0ull; w1[b] = 0ull; }
         }
-        const int valid = min(64, cnt - rb * 64);
-        const unsigned long long vmask = valid >= 64 ? ~0ull : ((1ull << valid) - 1ull);
-        const unsigned long long kept = ~cur & vmask;
-        if (lane == 0) s_kept = kept;
-        if ((kept >> lane) & 1ull) keep[sorted_idx[s0 + rb * 64 + lane]] = 1;
-        if ((kept >> (lane + 32)) & 1ull) keep[sorted_idx[s0 + rb * 64 + lane + 32]] = 1;
+#pragma unroll
+        for (int b = 0; b < kScanBatch; b++) {
+          if (b < nb) {
+            const int rb = rb0 + b;
+            while (s_progress <= rb) { }                                  // kept(rb) not published yet
+            __threadfence_block();
+            const unsigned long long k = s_kept[rb];
+            unsigned long long v = 0ull;
+            if ((k >> lane) & 1ull) v |= w0[b];
+            if ((k >> (lane + 32)) & 1ull) v |= w1[b];
+            acc_lo |= __reduce_or_sync(0xffffffffu, (unsigned)v);
+            acc_hi |= __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+          }
+        }
       }
-      __syncthreads();
-      const unsigned long long kept = s_kept;
-      for (int cb = rb + 1 + warp; cb < W; cb += kScanThreads / 32) {
-        const unsigned long long* tile = base + tri_index(W, rb, cb) * 64;
-        unsigned long long v = 0ull;
-        if ((kept >> lane) & 1ull) v |= tile[lane];
-        if ((kept >> (lane + 32)) & 1ull) v |= tile[lane + 32];
-        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
-        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-        if (lane == 0) s_remv[cb] |= ((unsigned long long)hi << 32) | lo;
+      // diagonal tile
+      const unsigned long long* diag = col + (size_t)cb * 64;
+      const unsigned long long d0 = diag[lane], d1 = diag[lane + 32];
+      unsigned long long cur = ((unsigned long long)acc_hi << 32) | acc_lo;
+      const unsigned nz0 = __ballot_sync(0xffffffffu, d0 != 0ull), nz1 = __ballot_sync(0xffffffffu, d1 != 0ull);
+      const unsigned long long nz = ((unsigned long long)nz1 << 32) | nz0;
+      unsigned long long done = 0ull;
+      for (;;) {
+        const unsigned long long cand = nz & ~cur & ~done;
+        if (!cand) break;
+        const int r = __ffsll((long long)cand) - 1;       // lowest kept row with a non-empty word
+        const unsigned long long wsel = (r < 32) ? d0 : d1;
+        const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)wsel, r & 31);
+        const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(wsel >> 32), r & 31);
+        cur |= ((unsigned long long)hi << 32) | lo;
+        done |= 1ull << r;
       }
-      __syncthreads();
+      const int valid = min(64, cnt - cb * 64);
+      const unsigned long long vmask = valid >= 64 ? ~0ull : ((1ull << valid) - 1ull);
+      const unsigned long long kept = ~cur & vmask;
+      if (lane == 0) {
+        while (s_progress < cb) { }                       // publish strictly in order
+        s_kept[cb] = kept;
+        __threadfence_block();
+        s_progress = cb + 1;
+      }
+      if ((kept >> lane) & 1ull) keep[sorted_idx[s0 + cb * 64 + lane]] = 1;
+      if ((kept >> (lane + 32)) & 1ull) keep[sorted_idx[s0 + cb * 64 + lane + 32]] = 1;
     }
   }
 }
@@ -384,7 +429,7 @@ JDET_API int jdet_nms_rotated(const float* dets, int n, int box_length, const in
     need = w.cub_bytes;
     JDET_RETURN_IF_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, need, w.seg_tiles, w.tile_base, n + 1, st));
   }
-  const size_t mask_smem = (size_t)(64 + kCH * 64) * sizeof(BoxRec) + (size_t)kCH * 64 * 2 * 4 + (size_t)kQCap * 2 * 2;
+  const size_t mask_smem = (size_t)(64 + kCH * 64) * sizeof(BoxRec) + 64 * 16 + (size_t)kCH * 64 * 2 * 4 + (size_t)kQCap * 2 * 2;
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_smem));
   nms_mask_kernel<<<kNumSMs * 3, kMaskThreads, mask_smem, st>>>(w.rec, w.seg_start, w.item_base, w.tile_base,
                                                         w.flag_scan, n, iou_threshold, label_in_pair,
