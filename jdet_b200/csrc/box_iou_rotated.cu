@@ -16,7 +16,10 @@
 //              survivors are recorded in a per-thread 32-bit mask, then compacted into a
 //              shared-memory queue with one warp scan + one atomic per warp.
 //     phase 2  queue -> SAT test -> second queue (warp-aggregated push).
-//     phase 3  second queue -> reference-exact clip/hull IoU with all lanes busy -> 4-B stores.
+//              The surviving (row, col) candidates are appended to a device-wide queue.
+// Kernel 3  iou_exact_kernel  one thread per queued candidate (grid-stride over the device-side count):
+//                             reference-exact clip/hull IoU with every lane busy and no barriers,
+//                             4-B stores over the zeros.  (Queue full => the tile CTA evaluates its own.)
 #include "common.cuh"
 #include "rbox_geom.cuh"
 
@@ -36,7 +39,8 @@ __global__ void __launch_bounds__(256) rec_kernel(const float* __restrict__ boxe
 template <int VERSION, bool VEC4>
 __global__ void __launch_bounds__(kThreads) iou_tile_kernel(const BoxRec* __restrict__ rec1, int n1,
                                                              const BoxRec* __restrict__ rec2, int n2,
-                                                             float* __restrict__ out) {
+                                                             float* __restrict__ out, int* __restrict__ gcount,
+                                                             uint2* __restrict__ gqueue, int gcap) {
   __shared__ BoxRec s_row[kTR];
   __shared__ BoxRec s_col[kTC];
   __shared__ __align__(16) float s_cx[kTC], s_cy[kTC], s_cr[kTC];
@@ -137,16 +141,42 @@ __global__ void __launch_bounds__(kThreads) iou_tile_kernel(const BoxRec* __rest
   }
   __syncthreads();
 
-  // ---- phase 3: exact IoU on the (few) real candidates ---------------------------------------
+  // ---- hand-off: candidates go to the device-wide queue drained by iou_exact_kernel (every lane of
+  // every warp busy there, no barriers); if the queue is full this CTA evaluates its own candidates.
   const int cnt2 = s_cnt2;
-  for (int k = tid; k < cnt2; k += kThreads) {
-    const unsigned short e = s_q2[k];
-    const int r = e >> 7, c = e & 127;
-    const BoxRec& A = s_row[r];
-    const BoxRec& B = s_col[c];
-    float v = 0.f;
-    if (A.tag == 0.f && B.tag == 0.f) v = iou_exact<VERSION>(A, B);
-    out[(size_t)(row0 + r) * n2 + (col0 + c)] = v;   // survivors are always in range (dead recs never survive)
+  __shared__ int s_base;
+  if (tid == 0) s_base = cnt2 > 0 ? atomicAdd(gcount, cnt2) : 0;
+  __syncthreads();
+  const int gbase = s_base;
+  if (gbase + cnt2 <= gcap) {
+    for (int k = tid; k < cnt2; k += kThreads) {
+      const unsigned short e = s_q2[k];
+      gqueue[gbase + k] = make_uint2((unsigned)(row0 + (e >> 7)), (unsigned)(col0 + (e & 127)));
+    }
+  } else {
+    for (int k = tid; k < cnt2; k += kThreads) {
+      if (gbase + k < gcap) gqueue[gbase + k] = make_uint2(0xffffffffu, 0u);   // reserved but unused slot
+      const unsigned short e = s_q2[k];
+      const int r = e >> 7, c = e & 127;
+      const BoxRec& A = s_row[r];
+      const BoxRec& B = s_col[c];
+      out[(size_t)(row0 + r) * n2 + (col0 + c)] = (A.tag == 0.f && B.tag == 0.f) ? iou_exact<VERSION>(A, B) : 0.f;
+    }
+  }
+}
+
+// Exact IoU for the queued candidates: one thread per pair, grid-stride over the device-side count.
+template <int VERSION>
+__global__ void __launch_bounds__(256) iou_exact_kernel(const BoxRec* __restrict__ rec1, const BoxRec* __restrict__ rec2,
+                                                         int n2, const int* __restrict__ gcount,
+                                                         const uint2* __restrict__ gqueue, int gcap,
+                                                         float* __restrict__ out) {
+  const int total = min(*gcount, gcap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint2 e = gqueue[i];
+    if (e.x == 0xffffffffu) continue;
+    const BoxRec A = rec1[e.x], B = rec2[e.y];
+    out[(size_t)e.x * n2 + e.y] = (A.tag == 0.f && B.tag == 0.f) ? iou_exact<VERSION>(A, B) : 0.f;
   }
 }
 
@@ -155,9 +185,17 @@ __global__ void __launch_bounds__(kThreads) iou_tile_kernel(const BoxRec* __rest
 // -------------------------------------------------------------------------------------------------
 // C ABI
 // -------------------------------------------------------------------------------------------------
+namespace jdet {
+static size_t iou_queue_cap(int n1, int n2) {
+  const long long pairs = (long long)n1 * n2;
+  return (size_t)(pairs < (16ll << 20) ? pairs : (16ll << 20));     // <= 128 MB of (row, col) candidates
+}
+}  // namespace jdet
+
 JDET_API size_t jdet_box_iou_rotated_workspace_bytes(int n1, int n2) {
-  return jdet_align_up((size_t)(n1 > 0 ? n1 : 0) * sizeof(jdet::BoxRec), 256) +
-         jdet_align_up((size_t)(n2 > 0 ? n2 : 0) * sizeof(jdet::BoxRec), 256);
+  if (n1 <= 0 || n2 <= 0) return 256;
+  return jdet_align_up((size_t)n1 * sizeof(jdet::BoxRec), 256) + jdet_align_up((size_t)n2 * sizeof(jdet::BoxRec), 256) +
+         256 + jdet_align_up(jdet::iou_queue_cap(n1, n2) * sizeof(uint2), 256);
 }
 
 // version 0: jdet.ops.box_iou_rotated      (ops/box_iou_rotated.py:502-509)
@@ -171,18 +209,27 @@ JDET_API int jdet_box_iou_rotated(const float* boxes1, int n1, const float* boxe
   if (!boxes1 || !boxes2 || !ious) return JDET_ERR_BAD_ARG;
   if (workspace_bytes < jdet_box_iou_rotated_workspace_bytes(n1, n2) || !workspace) return JDET_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  BoxRec* rec1 = (BoxRec*)workspace;
-  BoxRec* rec2 = (BoxRec*)((char*)workspace + jdet_align_up((size_t)n1 * sizeof(BoxRec), 256));
+  char* wsp = (char*)workspace;
+  BoxRec* rec1 = (BoxRec*)wsp;                 wsp += jdet_align_up((size_t)n1 * sizeof(BoxRec), 256);
+  BoxRec* rec2 = (BoxRec*)wsp;                 wsp += jdet_align_up((size_t)n2 * sizeof(BoxRec), 256);
+  int* gcount = (int*)wsp;                     wsp += 256;
+  uint2* gqueue = (uint2*)wsp;
+  const int gcap = (int)iou_queue_cap(n1, n2);
+  JDET_RETURN_IF_CUDA(cudaMemsetAsync(gcount, 0, 256, st));
   rec_kernel<<<jdet_ceil_div(n1, 256), 256, 0, st>>>(boxes1, n1, 5, version == 1, rec1);
   rec_kernel<<<jdet_ceil_div(n2, 256), 256, 0, st>>>(boxes2, n2, 5, version == 1, rec2);
   dim3 grid(jdet_ceil_div(n2, kTC), jdet_ceil_div(n1, kTR));
   const bool vec = (n2 % 4 == 0) && (((uintptr_t)ious & 15) == 0);
+  const long long pairs = (long long)n1 * n2;
+  const int xgrid = (int)(pairs < 256 * 1024 ? (pairs + 255) / 256 : kNumSMs * 8);
   if (version == 0) {
-    if (vec) iou_tile_kernel<0, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious);
-    else     iou_tile_kernel<0, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious);
+    if (vec) iou_tile_kernel<0, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap);
+    else     iou_tile_kernel<0, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap);
+    iou_exact_kernel<0><<<xgrid, 256, 0, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious);
   } else {
-    if (vec) iou_tile_kernel<1, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious);
-    else     iou_tile_kernel<1, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious);
+    if (vec) iou_tile_kernel<1, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap);
+    else     iou_tile_kernel<1, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap);
+    iou_exact_kernel<1><<<xgrid, 256, 0, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious);
   }
   return (int)cudaGetLastError();
 }

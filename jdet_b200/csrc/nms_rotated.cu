@@ -35,7 +35,8 @@ struct NmsWs {
   unsigned* keys_in; unsigned* keys_out; int* vals_in; int* vals_out;
   BoxRec* rec; int* sorted_idx; int* flags; int* flag_scan; int* seg_start;
   int* seg_items; int* item_base; long long* seg_tiles; long long* tile_base;
-  int* counters;                   // [0] work counter
+  int* counters;                   // [0] work counter, [1] candidate-queue count
+  uint4* xqueue; int xcap;         // device-wide exact-IoU candidate queue
   unsigned long long* mask; size_t mask_tiles;
   void* cub_temp; size_t cub_bytes;
 };
@@ -59,6 +60,8 @@ static size_t carve(NmsWs* w, void* base, int n) {
   w->counters = (int*)take(256);
   w->cub_bytes = (size_t)n * 16 + (1u << 20);
   w->cub_temp = take(w->cub_bytes);
+  w->xcap = (int)(((long long)n * n / 2 < (8ll << 20)) ? ((long long)n * n / 2 + 64) : (8ll << 20));
+  w->xqueue = (uint4*)take((size_t)w->xcap * sizeof(uint4));
   w->mask_tiles = mask_tile_bound(n);
   w->mask = (unsigned long long*)take(w->mask_tiles * 64 * 8);
   return off;
@@ -135,7 +138,8 @@ __device__ __forceinline__ long long tri_index(long long rb, long long cb) { ret
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     const BoxRec* __restrict__ rec, const int* __restrict__ seg_start, const int* __restrict__ item_base,
     const long long* __restrict__ tile_base, const int* __restrict__ scan, int n, float thr,
-    int label_in_pair, int* __restrict__ counter, unsigned long long* __restrict__ mask) {
+    int label_in_pair, int* __restrict__ counter, unsigned long long* __restrict__ mask,
+    uint4* __restrict__ xqueue, int xcap) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   BoxRec* s_row = reinterpret_cast<BoxRec*>(s_dyn);                       //  2 KB
   BoxRec* s_col = s_row + 64;                                             // 16 KB
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
   unsigned* s_bits = reinterpret_cast<unsigned*>(s_rowq + 64);            //  4 KB: tile words as (lo, hi)
   unsigned short* s_q1 = reinterpret_cast<unsigned short*>(s_bits + kCH * 64 * 2);   // 2 x kQCap entries
   unsigned short* s_q2 = s_q1 + kQCap;
-  __shared__ int s_cnt1, s_cnt2, s_item;
+  __shared__ int s_cnt1, s_cnt2, s_item, s_xbase;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int nseg = scan[n - 1];
@@ -249,7 +253,10 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
         bool keep = false; unsigned short e = 0;
         if (k < c1) {
           e = s_q1[k];
-          keep = label_in_pair ? true : !sat_disjoint<0>(s_row[(e >> 6) & 63], s_col[(e >> 12) * 64 + (e & 63)]);
+          const BoxRec& A = s_row[(e >> 6) & 63];
+          const BoxRec& B = s_col[(e >> 12) * 64 + (e & 63)];
+          // SAT reject, then the IoU upper bound: a pair that provably cannot exceed thr never reaches phase 3
+          keep = label_in_pair ? true : (!sat_disjoint<0>(A, B) && !(iou_upper_bound<0>(A, B) < thr));
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (bal) {
@@ -260,17 +267,33 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
         }
       }
       __syncthreads();
-      // ---- phase 3: exact IoU, strict > thr ----------------------------------------------------------
+      // ---- hand-off: exact-IoU candidates go to the device-wide queue (nms_exact_kernel: every lane busy,
+      // no barriers).  Queue full => this CTA evaluates its own candidates (phase 3 in place).
       const int c2 = s_cnt2;
-      for (int k = tid; k < c2; k += kMaskThreads) {
-        const unsigned short e = s_q2[k];
-        const int r = (e >> 6) & 63, tt = e >> 12, cc = e & 63;
-        const BoxRec& A = s_row[r];
-        const BoxRec& B = s_col[tt * 64 + cc];
-        float v;
-        if (label_in_pair && A.tag != B.tag) v = 0.f;   // nms_rotated.py:285-286
-        else v = iou_exact<0>(A, B);
-        if (v > thr) atomicOr(&s_bits[(tt * 64 + r) * 2 + (cc >> 5)], 1u << (cc & 31));
+      if (tid == 0) s_xbase = c2 > 0 ? atomicAdd(counter + 1, c2) : 0;
+      __syncthreads();
+      const int xbase = s_xbase;
+      const long long wbase = tile_base[seg] * 64;
+      if (xbase + c2 <= xcap) {
+        for (int k = tid; k < c2; k += kMaskThreads) {
+          const unsigned short e = s_q2[k];
+          const int r = (e >> 6) & 63, tt = e >> 12, cc = e & 63;
+          const long long word = wbase + tri_index(rb, cb0 + tt) * 64 + r;
+          xqueue[xbase + k] = make_uint4((unsigned)(s0 + rb * 64 + r), (unsigned)(s0 + (cb0 + tt) * 64 + cc),
+                                         (unsigned)(word & 0xffffffffll), (unsigned)((word >> 32) << 8) | (unsigned)cc);
+        }
+      } else {
+        for (int k = tid; k < c2; k += kMaskThreads) {
+          if (xbase + k < xcap) xqueue[xbase + k] = make_uint4(0xffffffffu, 0u, 0u, 0u);   // reserved, unused
+          const unsigned short e = s_q2[k];
+          const int r = (e >> 6) & 63, tt = e >> 12, cc = e & 63;
+          const BoxRec& A = s_row[r];
+          const BoxRec& B = s_col[tt * 64 + cc];
+          float v;
+          if (label_in_pair && A.tag != B.tag) v = 0.f;   // nms_rotated.py:285-286
+          else v = iou_exact<0>(A, B);
+          if (v > thr) atomicOr(&s_bits[(tt * 64 + r) * 2 + (cc >> 5)], 1u << (cc & 31));
+        }
       }
       __syncthreads();
       if (!pending) break;
@@ -282,6 +305,27 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     for (int k = tid; k < ncb * 64; k += kMaskThreads) {
       const int t = k >> 6, r = k & 63;
       mbase[tri_index(rb, cb0 + t) * 64 + r] = ((unsigned long long)s_bits[2 * k + 1] << 32) | s_bits[2 * k];
+    }
+  }
+}
+
+// ---- exact kernel --------------------------------------------------------------------------------
+// One thread per queued candidate: reference-exact IoU(higher-ranked, lower-ranked), strict "> thr",
+// bit set with a 64-bit atomicOr straight into the triangular mask written (as zeros) by the mask kernel.
+__global__ void __launch_bounds__(256) nms_exact_kernel(const BoxRec* __restrict__ rec, const int* __restrict__ counter,
+                                                         const uint4* __restrict__ xqueue, int xcap, float thr,
+                                                         int label_in_pair, unsigned long long* __restrict__ mask) {
+  const int total = min(counter[1], xcap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint4 e = xqueue[i];
+    if (e.x == 0xffffffffu) continue;
+    const BoxRec A = rec[e.x], B = rec[e.y];
+    float v;
+    if (label_in_pair && A.tag != B.tag) v = 0.f;
+    else v = iou_exact<0>(A, B);
+    if (v > thr) {
+      const unsigned long long word = ((unsigned long long)(e.w >> 8) << 32) | e.z;
+      atomicOr(mask + word, 1ull << (e.w & 63u));
     }
   }
 }
@@ -433,7 +477,8 @@ JDET_API int jdet_nms_rotated(const float* dets, int n, int box_length, const in
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_smem));
   nms_mask_kernel<<<kNumSMs * 3, kMaskThreads, mask_smem, st>>>(w.rec, w.seg_start, w.item_base, w.tile_base,
                                                         w.flag_scan, n, iou_threshold, label_in_pair,
-                                                        w.counters, w.mask);
+                                                        w.counters, w.mask, w.xqueue, w.xcap);
+  nms_exact_kernel<<<kNumSMs * 8, 256, 0, st>>>(w.rec, w.counters, w.xqueue, w.xcap, iou_threshold, label_in_pair, w.mask);
   const size_t smem = (size_t)jdet_ceil_div(n, 64) * 8;
   if (smem > 48 * 1024)
     JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
