@@ -83,6 +83,41 @@ __global__ void __launch_bounds__(256) feature_refine_kernel(const float* __rest
   }
 }
 
+// points == 1, W % 4 == 0: a thread owns 4 consecutive pixels, so the centre read and the store are
+// 16-B vectors (4x the bytes in flight per load instruction: the op is an HBM stream whose speed is
+// set by memory-level parallelism); the 4 x 4 taps stay scalar L1 gathers.
+__global__ void __launch_bounds__(256) feature_refine_p1_vec4_kernel(const float* __restrict__ feat,
+                                                                     const float* __restrict__ boxes, int C, int H, int W,
+                                                                     float spatial_scale, int ch_per_cta,
+                                                                     float* __restrict__ out) {
+  const int HW = H * W;
+  const int p = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
+  if (p >= HW) return;
+  Tap4 t[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float* bb = boxes + ((size_t)n * HW + p + j) * 5;
+    t[j] = fr_tap(__fmul_rn(__ldg(bb), spatial_scale), __fmul_rn(__ldg(bb + 1), spatial_scale), H, W);
+  }
+  const float* plane = feat + ((size_t)n * C + c0) * HW;
+  float* dst = out + ((size_t)n * C + c0) * HW + p;
+#pragma unroll 2
+  for (int c = c0; c < c1; c++) {
+    const float4 ctr = __ldg(reinterpret_cast<const float4*>(plane + p));
+    float v[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (t[j].o00 >= 0)
+        v[j] += t[j].w1 * __ldg(plane + t[j].o00) + t[j].w2 * __ldg(plane + t[j].o01) + t[j].w3 * __ldg(plane + t[j].o10) +
+                t[j].w4 * __ldg(plane + t[j].o11);
+    st_stream_v4(dst, v[0], v[1], v[2], v[3]);
+    plane += HW;
+    dst += HW;
+  }
+}
+
 }  // namespace jdet
 
 // jdet.ops.fr.feature_refine(features, best_rbboxes, spatial_scale, points) (ops/fr.py:255-273)
@@ -100,7 +135,13 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
   int ch_per_cta = C;
   while (ch_per_cta > 16 && (long long)ptiles * jdet_ceil_div(C, ch_per_cta) * N < 148 * 8) ch_per_cta = (ch_per_cta + 1) / 2;
   dim3 grid(ptiles, jdet_ceil_div(C, ch_per_cta), N);
-  if (points == 1) feature_refine_kernel<1><<<grid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, output);
+  if (points == 1 && W % 4 == 0 && (((uintptr_t)features | (uintptr_t)output) & 15) == 0) {
+    const int vt = jdet_ceil_div(HW / 4, 256);
+    int cpc = C;
+    while (cpc > 16 && (long long)vt * jdet_ceil_div(C, cpc) * N < 148 * 8) cpc = (cpc + 1) / 2;
+    dim3 vgrid(vt, jdet_ceil_div(C, cpc), N);
+    feature_refine_p1_vec4_kernel<<<vgrid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, cpc, output);
+  } else if (points == 1) feature_refine_kernel<1><<<grid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, output);
   else             feature_refine_kernel<5><<<grid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, output);
   return (int)cudaGetLastError();
 }
