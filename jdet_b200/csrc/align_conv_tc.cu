@@ -8,7 +8,7 @@
 // B200 design (no offsets tensor, no columns tensor):
 //   D[pixel, co] = sum_k A[pixel, k] * Wt[co, k],  k = tap*C + c  (tap-major K; weights re-packed once)
 //   M tile = 128 output pixels, N = Co (<= 256, the whole output-channel extent), K block = 32.
-//   A operand  : produced in-kernel.  4 producer warps derive the 9 sampling points of each pixel
+//   A operand  : produced in-kernel.  8 producer warps derive the 9 sampling points of each pixel
 //                straight from its refined anchor (same fp32 op order as get_offset + im2col), gather
 //                the 4 bilinear corners from a channel-last copy of x with 16-B loads (8 lanes = 32
 //                channels = one 128-B row), interpolate in fp32, split each value into two TF32 terms
@@ -22,8 +22,8 @@
 //                epilogue of tile i overlaps the main loop of tile i+1.
 //   Epilogue   : 4 warps, tcgen05.ld 32x32b -> ReLU -> NCHW stores (a warp writes 128 contiguous bytes
 //                per output channel).
-//   Persistent : grid = min(#tiles, 148); warp roles: 0-3 epilogue, 4-7 A producers, 8 MMA + TMEM
-//                alloc, 9 B loader.  Barriers are mbarriers (full/empty per smem stage, full/empty per
+//   Persistent : grid = min(#tiles, 148); warp roles: 0-3 epilogue, 4-11 A producers, 12 MMA + TMEM
+//                alloc, then the B loader.  Barriers are mbarriers (full/empty per smem stage, full/empty per
 //                TMEM accumulator stage).
 //
 // Layout in HBM: x (N,C,H,W) fp32 -> channel-last scratch (N,H,W,C); anchors (N,H,W,5); weight
@@ -36,7 +36,10 @@ void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cuda
 
 namespace tc {
 
-constexpr int kThreads = 320;
+constexpr int kProdWarps = 8;                 // A-producer warps (4 pixels x 8 channel-quad lanes per warp step)
+constexpr int kPix = 128 / (kProdWarps * 4);  // pixels per lane per stage
+constexpr int kMmaWarp = 4 + kProdWarps, kLoadWarp = 5 + kProdWarps;
+constexpr int kThreads = (6 + kProdWarps) * 32;
 constexpr int kStages = 2;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;                 // fp32 elements = one 128-B swizzle row
@@ -146,12 +149,12 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
   const int cblocks = p.C / 32;
   const int num_kb = 9 * cblocks;
 
-  if (warp == 9 && lane == 0) {
-    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 5); mbar_init(&empty[s], 1); }
+  if (warp == kLoadWarp && lane == 0) {
+    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], kProdWarps + 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -160,17 +163,17 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < 4 + kProdWarps) {
     // =============================== A producers ==============================================
     const int pw = warp - 4, sp = lane >> 3, q = lane & 7;
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       // per-pixel anchor geometry (s2anet_head.py:689-698), 8 pixels per lane
-      float gx[8], gy[8], gdw[8], gdh[8], gc[8], gs[8], fh[8], fw[8];
-      long long pbase[8];          // n * HW (pixel index of the image origin), -1 => row beyond the tensor
+      float gx[kPix], gy[kPix], gdw[kPix], gdh[kPix], gc[kPix], gs[kPix], fh[kPix], fw[kPix];
+      long long pbase[kPix];          // n * HW (pixel index of the image origin), -1 => row beyond the tensor
 #pragma unroll
-      for (int it = 0; it < 8; it++) {
-        const int r = pw * 32 + it * 4 + sp;
+      for (int it = 0; it < kPix; it++) {
+        const int r = pw * (4 * kPix) + it * 4 + sp;
         const long long pix = (long long)tile * kBlockM + r;
         if (pix < P) {
           const int n = (int)(pix / HW), hw = (int)(pix - (long long)n * HW);
@@ -193,11 +196,11 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
       }
       for (int t = 0; t < 9; t++) {
         // tap geometry once per tap, reused by the C/32 channel blocks
-        int o00[8], o01[8], o10[8], o11[8];
-        float w1[8], w2[8], w3[8], w4[8];
+        int o00[kPix], o01[kPix], o10[kPix], o11[kPix];
+        float w1[kPix], w2[kPix], w3[kPix], w4[kPix];
         const float xx = (float)(t % 3 - 1), yy = (float)(t / 3 - 1);
 #pragma unroll
-        for (int it = 0; it < 8; it++) {
+        for (int it = 0; it < kPix; it++) {
           const float x = __fmul_rn(gdw[it], xx), y = __fmul_rn(gdh[it], yy);
           const float xr = __fsub_rn(__fmul_rn(gc[it], x), __fmul_rn(gs[it], y));
           const float yr = __fadd_rn(__fmul_rn(gs[it], x), __fmul_rn(gc[it], y));
@@ -223,9 +226,9 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* ah = a_hi(stage);
           unsigned char* al = a_lo(stage);
-          float4 v[8];
+          float4 v[kPix];
 #pragma unroll
-          for (int it = 0; it < 8; it++) {
+          for (int it = 0; it < kPix; it++) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 a = z, b = z, c = z, d = z;
             if (pbase[it] >= 0) {
@@ -242,8 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
             v[it].w = w1[it] * a.w + w2[it] * b.w + w3[it] * c.w + w4[it] * d.w;
           }
 #pragma unroll
-          for (int it = 0; it < 8; it++) {
-            const int r = pw * 32 + it * 4 + sp;
+          for (int it = 0; it < kPix; it++) {
+            const int r = pw * (4 * kPix) + it * 4 + sp;
             const uint32_t off = (uint32_t)r * 128u + (uint32_t)((q ^ (r & 7)) << 4);
             float4 h4, l4;
             h4.x = __uint_as_float(__float_as_uint(v[it].x) & 0xffffe000u); l4.x = v[it].x - h4.x;
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kLoadWarp) {
     // =============================== B loader ==================================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // =============================== MMA issuer =================================================
     // instruction descriptor: D=F32, A=B=TF32, K-major both, N = Co, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }

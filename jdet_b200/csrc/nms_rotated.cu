@@ -201,12 +201,17 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     // ---- phase 1 ---------------------------------------------------------------------------------
     unsigned long long m[2] = {0ull, 0ull};               // bit r: (row r, my column j) survives
     if (!label_in_pair) {
-#pragma unroll 8
-      for (int r = 0; r < 64; r++) {
-        const float4 rq = s_rowq[r];
-        m[0] |= (unsigned long long)(circle_disjoint(rq.x, rq.y, rq.z, cx[0], cy[0], cq[0]) ? 0u : 1u) << r;
-        m[1] |= (unsigned long long)(circle_disjoint(rq.x, rq.y, rq.z, cx[1], cy[1], cq[1]) ? 0u : 1u) << r;
+      unsigned w00 = 0u, w01 = 0u, w10 = 0u, w11 = 0u;   // [column j][row half]: constant shifts after unrolling
+#pragma unroll
+      for (int r = 0; r < 32; r++) {
+        const float4 ra = s_rowq[r], rb2 = s_rowq[r + 32];
+        w00 |= (circle_disjoint(ra.x, ra.y, ra.z, cx[0], cy[0], cq[0]) ? 0u : 1u) << r;
+        w10 |= (circle_disjoint(ra.x, ra.y, ra.z, cx[1], cy[1], cq[1]) ? 0u : 1u) << r;
+        w01 |= (circle_disjoint(rb2.x, rb2.y, rb2.z, cx[0], cy[0], cq[0]) ? 0u : 1u) << r;
+        w11 |= (circle_disjoint(rb2.x, rb2.y, rb2.z, cx[1], cy[1], cq[1]) ? 0u : 1u) << r;
       }
+      m[0] = ((unsigned long long)w01 << 32) | w00;
+      m[1] = ((unsigned long long)w11 << 32) | w10;
     } else {
       const int nrow = min(64, cnt - rb * 64);
       const unsigned long long rows = nrow >= 64 ? ~0ull : ((1ull << nrow) - 1ull);
@@ -337,9 +342,9 @@ __global__ void __launch_bounds__(256) nms_exact_kernel(const BoxRec* __restrict
 // ballots, writes the keep flags, and publishes kept(cb) + a progress counter through shared
 // memory.  Loads never depend on kept(), so each warp prefetches a batch of tiles and only the
 // masking waits; the serial chain per block is "apply tile (cb-1, cb) -> resolve diag -> publish".
-constexpr int kScanWarps = 16;
+constexpr int kScanWarps = 24;
 constexpr int kScanThreads = kScanWarps * 32;
-constexpr int kScanBatch = 8;
+constexpr int kScanBatch = 12;
 
 __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(
     const int* __restrict__ seg_start, const long long* __restrict__ tile_base, const int* __restrict__ scan,
