@@ -36,7 +36,7 @@ void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cuda
 
 namespace tc {
 
-constexpr int kProdWarps = 8;                 // A-producer warps (4 pixels x 8 channel-quad lanes per warp step)
+constexpr int kProdWarps = 16;                // A-producer warps (4 pixels x 8 channel-quad lanes per warp step)
 constexpr int kPix = 128 / (kProdWarps * 4);  // pixels per lane per stage
 constexpr int kMmaWarp = 4 + kProdWarps, kLoadWarp = 5 + kProdWarps;
 constexpr int kThreads = (6 + kProdWarps) * 32;
