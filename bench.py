@@ -30,6 +30,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 L2_FLUSH_BYTES = 256 << 20
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def load_peaks():
@@ -214,7 +221,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_extra:
         line["cpu_baseline"] = cpu_baseline_roi(feat.cpu().numpy(), rois_h)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -386,10 +393,16 @@ def run_reference(args):
                              "sample": "%d RoIs per step x %d steps; the reference has no CPU path for roi_align_rotated "
                                        "(CUDA-only), so this is oracle/oracle.cpp (OpenMP over RoIs)" % (sample, K)},
             "e2e": {"value": v, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
+    # Libraries (NCCL prints its version banner to stdout) must not pollute the ONE JSON line the driver
+    # parses: route fd 1 to stderr for the whole run and keep the real stdout for the final line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
