@@ -27,9 +27,10 @@
 
 namespace jdet {
 
-constexpr int kCH = 8;             // column blocks per work item
+constexpr int kCH = 16;            // column blocks per work item (64 rows x 1024 columns)
+constexpr int kColsPerThread = kCH * 64 / 256;
 constexpr int kMaskThreads = 256;
-constexpr int kQCap = 8192;        // survivor queue entries per CTA
+constexpr int kQCap = 4096;        // survivor queue entries per CTA (overflow => extra rounds)
 
 struct NmsWs {
   unsigned* keys_in; unsigned* keys_out; int* vals_in; int* vals_out;
@@ -67,10 +68,14 @@ static size_t carve(NmsWs* w, void* base, int n) {
   return off;
 }
 
+// 8-bit GROUPING key of a label: segments only have to bring equal labels together (one radix pass
+// instead of four); labels that share a key are told apart by the tag comparison in phase 2, exactly
+// as the reference's `box1_raw[5] != box2_raw[5]` does.  Small integer class ids map to distinct keys.
 __device__ __forceinline__ unsigned label_key(float l) {
   if (l == 0.f) l = 0.f;                       // -0.0 == +0.0 under the reference's != test
-  unsigned u = __float_as_uint(l);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  if (l >= 0.f && l < 16777216.f && l == truncf(l)) return ((unsigned)l) & 255u;
+  const unsigned u = __float_as_uint(l);
+  return (u ^ (u >> 8) ^ (u >> 16) ^ (u >> 24)) & 255u;
 }
 
 __global__ void key_kernel(const float* __restrict__ dets, const int* __restrict__ order, int n,
@@ -181,10 +186,10 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
       s_row[tid] = r;
       s_rowq[tid] = make_float4(r.x, r.y, r.qr, 0.f);
     }
-    // this thread's two columns stay in registers for phase 1
-    float cx[2], cy[2], cq[2];
+    // this thread's columns stay in registers for phase 1
+    float cx[kColsPerThread], cy[kColsPerThread], cq[kColsPerThread];
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
+    for (int j = 0; j < kColsPerThread; j++) {
       const int c = tid + j * kMaskThreads;
       BoxRec r = dead;
       if (c < ncols) {
@@ -199,32 +204,35 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     __syncthreads();
 
     // ---- phase 1 ---------------------------------------------------------------------------------
-    unsigned long long m[2] = {0ull, 0ull};               // bit r: (row r, my column j) survives
+    unsigned long long m[kColsPerThread];                 // bit r: (row r, my column j) survives
     if (!label_in_pair) {
-      unsigned w00 = 0u, w01 = 0u, w10 = 0u, w11 = 0u;   // [column j][row half]: constant shifts after unrolling
+      unsigned wlo[kColsPerThread], whi[kColsPerThread];  // constant shifts after unrolling
+#pragma unroll
+      for (int j = 0; j < kColsPerThread; j++) { wlo[j] = 0u; whi[j] = 0u; }
 #pragma unroll
       for (int r = 0; r < 32; r++) {
         const float4 ra = s_rowq[r], rb2 = s_rowq[r + 32];
-        w00 |= (circle_disjoint(ra.x, ra.y, ra.z, cx[0], cy[0], cq[0]) ? 0u : 1u) << r;
-        w10 |= (circle_disjoint(ra.x, ra.y, ra.z, cx[1], cy[1], cq[1]) ? 0u : 1u) << r;
-        w01 |= (circle_disjoint(rb2.x, rb2.y, rb2.z, cx[0], cy[0], cq[0]) ? 0u : 1u) << r;
-        w11 |= (circle_disjoint(rb2.x, rb2.y, rb2.z, cx[1], cy[1], cq[1]) ? 0u : 1u) << r;
+#pragma unroll
+        for (int j = 0; j < kColsPerThread; j++) {
+          wlo[j] |= (circle_disjoint(ra.x, ra.y, ra.z, cx[j], cy[j], cq[j]) ? 0u : 1u) << r;
+          whi[j] |= (circle_disjoint(rb2.x, rb2.y, rb2.z, cx[j], cy[j], cq[j]) ? 0u : 1u) << r;
+        }
       }
-      m[0] = ((unsigned long long)w01 << 32) | w00;
-      m[1] = ((unsigned long long)w11 << 32) | w10;
+#pragma unroll
+      for (int j = 0; j < kColsPerThread; j++) m[j] = ((unsigned long long)whi[j] << 32) | wlo[j];
     } else {
       const int nrow = min(64, cnt - rb * 64);
       const unsigned long long rows = nrow >= 64 ? ~0ull : ((1ull << nrow) - 1ull);
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
+      for (int j = 0; j < kColsPerThread; j++) {
         const int c = tid + j * kMaskThreads;
-        if (c < ncols && cb0 * 64 + c < cnt) m[j] = rows;
+        m[j] = (c < ncols && cb0 * 64 + c < cnt) ? rows : 0ull;
       }
     }
     // strictly upper triangle: in the diagonal tile (cb == rb) column c only meets rows r < c
     if (cb0 == rb) {
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
+      for (int j = 0; j < kColsPerThread; j++) {
         const int c = tid + j * kMaskThreads;
         if (c < 64) m[j] &= (c == 0) ? 0ull : ((1ull << c) - 1ull);
       }
@@ -232,7 +240,9 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     // Survivors -> queue.  Candidates per item are normally a few hundred; if they exceed kQCap the
     // remainder stays in the per-thread masks and goes through another round of phases 2 and 3.
     for (;;) {
-      const int want = __popcll(m[0]) + __popcll(m[1]);
+      int want = 0;
+#pragma unroll
+      for (int j = 0; j < kColsPerThread; j++) want += __popcll(m[j]);
       int incl = want;                                   // warp inclusive scan, one atomic per warp
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
       base = __shfl_sync(0xffffffffu, base, 31);
       int pos = base + incl - want;
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
+      for (int j = 0; j < kColsPerThread; j++) {
         const int c = tid + j * kMaskThreads;
         while (m[j] && pos < kQCap) {
           const int r = __ffsll((long long)m[j]) - 1;
@@ -250,7 +260,10 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
           s_q1[pos++] = (unsigned short)(((c >> 6) << 12) | (r << 6) | (c & 63));
         }
       }
-      const int pending = __syncthreads_or((m[0] | m[1]) != 0ull);
+      unsigned long long left = 0ull;
+#pragma unroll
+      for (int j = 0; j < kColsPerThread; j++) left |= m[j];
+      const int pending = __syncthreads_or(left != 0ull);
       const int c1 = min(s_cnt1, kQCap);
       // ---- phase 2: SAT ----------------------------------------------------------------------------
       for (int b0 = 0; b0 < c1; b0 += kMaskThreads) {
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
           const BoxRec& A = s_row[(e >> 6) & 63];
           const BoxRec& B = s_col[(e >> 12) * 64 + (e & 63)];
           // SAT reject, then the IoU upper bound: a pair that provably cannot exceed thr never reaches phase 3
-          keep = label_in_pair ? true : (!sat_disjoint<0>(A, B) && !(iou_upper_bound<0>(A, B) < thr));
+          keep = label_in_pair ? true : (A.tag == B.tag && !sat_disjoint<0>(A, B) && !(iou_upper_bound<0>(A, B) < thr));
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (bal) {
@@ -363,6 +376,10 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(
     __syncthreads();
     for (int cb = warp; cb < W; cb += kScanWarps) {
       const unsigned long long* col = base + tri_index(0, cb) * 64;     // tiles (0..cb, cb), contiguous
+      // the diagonal tile and the scatter indices do not depend on anything: fetch them before the chain
+      const unsigned long long d0 = col[(size_t)cb * 64 + lane], d1 = col[(size_t)cb * 64 + lane + 32];
+      const int p0 = cb * 64 + lane, p1 = p0 + 32;
+      const int idx0 = p0 < cnt ? sorted_idx[s0 + p0] : 0, idx1 = p1 < cnt ? sorted_idx[s0 + p1] : 0;
       unsigned acc_lo = 0u, acc_hi = 0u;
       for (int rb0 = 0; rb0 < cb; rb0 += kScanBatch) {
         const int nb = min(kScanBatch, cb - rb0);
@@ -388,8 +405,6 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(
         }
       }
       // diagonal tile
-      const unsigned long long* diag = col + (size_t)cb * 64;
-      const unsigned long long d0 = diag[lane], d1 = diag[lane + 32];
       unsigned long long cur = ((unsigned long long)acc_hi << 32) | acc_lo;
       const unsigned nz0 = __ballot_sync(0xffffffffu, d0 != 0ull), nz1 = __ballot_sync(0xffffffffu, d1 != 0ull);
       const unsigned long long nz = ((unsigned long long)nz1 << 32) | nz0;
@@ -413,8 +428,8 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(
         __threadfence_block();
         s_progress = cb + 1;
       }
-      if ((kept >> lane) & 1ull) keep[sorted_idx[s0 + cb * 64 + lane]] = 1;
-      if ((kept >> (lane + 32)) & 1ull) keep[sorted_idx[s0 + cb * 64 + lane + 32]] = 1;
+      if ((kept >> lane) & 1ull) keep[idx0] = 1;
+      if ((kept >> (lane + 32)) & 1ull) keep[idx1] = 1;
     }
   }
 }
@@ -454,11 +469,11 @@ JDET_API int jdet_nms_rotated(const float* dets, int n, int box_length, const in
   if (segment) {
     key_kernel<<<G, T, 0, st>>>(dets, order, n, w.keys_in, w.vals_in);
     size_t need = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, need, w.keys_in, w.keys_out, w.vals_in, w.vals_out, n, 0, 32, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, need, w.keys_in, w.keys_out, w.vals_in, w.vals_out, n, 0, 8, st);
     if (need > w.cub_bytes) return JDET_ERR_WORKSPACE;
     need = w.cub_bytes;
     JDET_RETURN_IF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, need, w.keys_in, w.keys_out, w.vals_in,
-                                                       w.vals_out, n, 0, 32, st));
+                                                       w.vals_out, n, 0, 8, st));
     pos = w.vals_out;
   }
   gather_kernel<<<G, T, 0, st>>>(dets, box_length, order, pos, w.keys_out, n, label_in_pair, w.rec,

@@ -22,6 +22,7 @@
 //
 // Layout in HBM: input (B,C,H,W) fp32; rois (R,6) = [batch, cx, cy, w, h, theta]; output
 // (R,C,PH,PW) fp32; workspace: channel-last copy (B*H*W*C fp32) for the staged path.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace jdet {
@@ -251,15 +252,17 @@ JDET_API int jdet_roi_align_rotated(int version, const float* input, int B, int 
     float* nhwc = (float*)workspace;
     launch_nchw_to_nhwc(input, nhwc, B, C, H * W, st);
     const size_t smem = (size_t)nbins * sampling_ratio * sampling_ratio * sizeof(SampleTap) + (size_t)64 * nbins * 4;
+    const char* gv = getenv("JDET_ROI_THREADS");
+    const int kGatherThreads = gv ? atoi(gv) : 256;
     dim3 grid(R, C / 64);
     // (measured alternatives on B200, cfg2: one CTA per RoI over all channels 163 us; per-bin tap merging
     //  185-250 us; this shape 146 us — smaller CTAs keep more of them resident and hide the gather latency)
     if (version == 1) {
       if (smem > 48 * 1024) JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_align_nhwc_kernel<1><<<grid, 256, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);
+      roi_align_nhwc_kernel<1><<<grid, kGatherThreads, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);
     } else {
       if (smem > 48 * 1024) JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_align_nhwc_kernel<0><<<grid, 256, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);
+      roi_align_nhwc_kernel<0><<<grid, kGatherThreads, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);
     }
   } else {
     const int ch_per_cta = 32;

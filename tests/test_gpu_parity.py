@@ -156,6 +156,15 @@ def test_nms_strict_threshold_and_corner_cases():
     st = np.full(200, 0.5, np.float32)
     got = nr.ml_nms_rotated(cu(dd), cu(st), cu(ll, torch.int64), 0.2).cpu().numpy()
     assert np.array_equal(got, oracle.ml_nms_rotated(dd, st, ll, 0.2, oracle.VARIANT_CUDA))
+    # more distinct labels than grouping keys (8-bit hash), non-integer and negative label values:
+    # boxes that share a key but not a label must still never interact
+    d4 = clustered_boxes(rng, 3000, 60, 300.0)
+    lab = rng.choice(np.concatenate([np.arange(0, 700, dtype=np.float32), np.array([-3.0, 0.5, 1e9, -0.0], np.float32),
+                                     (np.arange(40) + 0.25).astype(np.float32)]), 3000).astype(np.float32)
+    d6 = np.concatenate([d4, lab[:, None]], 1).astype(np.float32)
+    order = oracle.argsort_desc(tie_free_scores(rng, 3000))
+    got = nr.nms_rotated_cuda(cu(d6), cu(order, torch.int32), 0.15, box_length=6).cpu().numpy()
+    assert np.array_equal(got, oracle.nms_rotated_keep(d6, order, 0.15, oracle.VARIANT_CUDA))
     # degenerate boxes never suppress nor get suppressed
     deg = np.array([[5, 5, 0, 0, 0], [5, 5, 0, 0, 0], [5, 5, 3, 3, 0], [5, 5, 3, 3, 0.01]], np.float32)
     assert nr.nms_rotated(cu(deg), cu([0.9, 0.8, 0.7, 0.6]), 0.1).tolist() == [0, 1, 2]
