@@ -43,7 +43,7 @@ __device__ __forceinline__ Tap4 fr_tap(float y, float x, int H, int W) {
 
 // grid = (pixel tiles of 256, channel slabs, N)
 template <int POINTS>
-__global__ void __launch_bounds__(256, 2) feature_refine_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
+__global__ void __launch_bounds__(256, 3) feature_refine_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
                                                               int C, int H, int W, float spatial_scale, int ch_per_cta,
                                                               float* __restrict__ out) {
   const int HW = H * W;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256, 2) feature_refine_kernel(const float* __r
   }
   const float* plane = feat + ((size_t)n * C + c0) * HW;
   float* dst = out + ((size_t)n * C + c0) * HW + p;
-#pragma unroll 4
+#pragma unroll 2
   for (int c = c0; c < c1; c++) {
     float v = __ldg(plane + p);
 #pragma unroll
