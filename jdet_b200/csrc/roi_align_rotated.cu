@@ -14,15 +14,14 @@
 //                  reused by every channel (256x at the bench shape).
 //   staged path    (dense RoI sets) the NCHW map is re-laid once as channel-last (B,H,W,C) in the
 //                  caller's workspace (tiled smem transpose, both sides coalesced); the gather
-//                  kernel then reads every tap as 16-B vectors over channels: a half-warp covers
-//                  256 contiguous bytes of one pixel.  Output slab (64 ch x PH*PW) is assembled
+//                  kernel then reads every tap as 16-B vectors over channels: a warp covers 512
+//                  contiguous bytes of one pixel.  Output slab (128 ch x PH*PW) is assembled
 //                  in smem and written with coalesced 16-B streaming stores.
 //   direct path    (few RoIs on a big map, where re-laying the map would cost more than it saves)
 //                  NCHW gathers with the hoisted table; lanes run along the bins of one channel.
 //
 // Layout in HBM: input (B,C,H,W) fp32; rois (R,6) = [batch, cx, cy, w, h, theta]; output
 // (R,C,PH,PW) fp32; workspace: channel-last copy (B*H*W*C fp32) for the staged path.
-#include <cstdlib>
 #include "common.cuh"
 
 namespace jdet {
@@ -110,30 +109,31 @@ __device__ __forceinline__ SampleTap make_tap(const RoiGeom& g, int ph, int pw, 
 void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cudaStream_t st);   // relayout.cu
 
 // ---- staged gather kernel ----------------------------------------------------------------------
-// grid = (R, C/64 slabs); 256 threads.  Requires C % 64 == 0 and PH*PW*gh*gw <= kMaxSamples
-// (sampling_ratio > 0).  Thread task = (bin, channel quad): 16 lanes span the slab's 64 channels.
-template <int VERSION>
+// grid = (R, C/SLAB slabs); 256 threads.  Requires C % 64 == 0 and PH*PW*gh*gw <= kMaxSamples
+// (sampling_ratio > 0).  Thread task = (bin, channel quad): SLAB/4 lanes span the slab's channels.
+template <int VERSION, int SLAB>
 __global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const float* __restrict__ feat_nhwc,
                                                               const float* __restrict__ rois, int C, int H, int W,
                                                               int PH, int PW, float spatial_scale, int sample_num,
                                                               float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int nbins = PH * PW;
-  const int r = blockIdx.x, c0 = blockIdx.y * 64;
+  const int r = blockIdx.x, c0 = blockIdx.y * SLAB;
+  constexpr int QL = SLAB / 4;                      // lanes (channel quads) per bin
   __shared__ RoiGeom g;
   if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)r * 6, spatial_scale, sample_num, PH, PW);
   __syncthreads();
   const int spb = g.gh * g.gw;                       // samples per bin
   SampleTap* taps = reinterpret_cast<SampleTap*>(smem);
-  float* s_out = reinterpret_cast<float*>(taps + nbins * spb);   // [64][nbins]
+  float* s_out = reinterpret_cast<float*>(taps + nbins * spb);   // [SLAB][nbins]
   for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
     const int bin = s / spb, k = s - bin * spb;
     taps[s] = make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
   }
   __syncthreads();
   const float* base = feat_nhwc + (size_t)g.batch * H * W * C + c0;
-  const int q = threadIdx.x & 15;                   // channel quad within the slab
-  for (int bin = threadIdx.x >> 4; bin < nbins; bin += blockDim.x >> 4) {
+  const int q = threadIdx.x % QL;                   // channel quad within the slab
+  for (int bin = threadIdx.x / QL; bin < nbins; bin += blockDim.x / QL) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const SampleTap* tp = taps + bin * spb;
     for (int k = 0; k < spb; k++) {
@@ -155,9 +155,9 @@ __global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const float* __rest
     s_out[(4 * q + 3) * nbins + bin] = acc.w / cnt;
   }
   __syncthreads();
-  // out[r][c0 .. c0+63][bins] is one contiguous run of 64*nbins floats
+  // out[r][c0 .. c0+SLAB-1][bins] is one contiguous run of SLAB*nbins floats
   float* dst = out + ((size_t)r * C + c0) * nbins;
-  const int total = 64 * nbins;
+  const int total = SLAB * nbins;
   if ((total & 3) == 0 && ((((size_t)r * C + c0) * nbins) & 3) == 0) {
     for (int i = threadIdx.x * 4; i < total; i += blockDim.x * 4)
       st_stream_v4(dst + i, s_out[i], s_out[i + 1], s_out[i + 2], s_out[i + 3]);
@@ -251,19 +251,20 @@ JDET_API int jdet_roi_align_rotated(int version, const float* input, int B, int 
     if (!workspace || workspace_bytes < need) return JDET_ERR_WORKSPACE;
     float* nhwc = (float*)workspace;
     launch_nchw_to_nhwc(input, nhwc, B, C, H * W, st);
-    const size_t smem = (size_t)nbins * sampling_ratio * sampling_ratio * sizeof(SampleTap) + (size_t)64 * nbins * 4;
-    const char* gv = getenv("JDET_ROI_THREADS");
-    const int kGatherThreads = gv ? atoi(gv) : 256;
-    dim3 grid(R, C / 64);
+    const int slab = (C % 128 == 0) ? 128 : 64;      // 128: one bin per warp, 512 contiguous bytes per tap
+    const size_t smem = (size_t)nbins * sampling_ratio * sampling_ratio * sizeof(SampleTap) + (size_t)slab * nbins * 4;
+    dim3 grid(R, C / slab);
     // (measured alternatives on B200, cfg2: one CTA per RoI over all channels 163 us; per-bin tap merging
-    //  185-250 us; this shape 146 us — smaller CTAs keep more of them resident and hide the gather latency)
-    if (version == 1) {
-      if (smem > 48 * 1024) JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_align_nhwc_kernel<1><<<grid, kGatherThreads, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);
-    } else {
-      if (smem > 48 * 1024) JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_align_nhwc_kernel<0><<<grid, kGatherThreads, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);
-    }
+    //  185-250 us; 64-channel slabs 146 us, with 128/192/64-thread CTAs 144/150/178 us; 128-channel slabs 136 us)
+#define JDET_LAUNCH_ROI(V, S)                                                                                          \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024)                                                                                              \
+      JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    roi_align_nhwc_kernel<V, S><<<grid, 256, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);          \
+  } while (0)
+    if (version == 1) { if (slab == 128) JDET_LAUNCH_ROI(1, 128); else JDET_LAUNCH_ROI(1, 64); }
+    else              { if (slab == 128) JDET_LAUNCH_ROI(0, 128); else JDET_LAUNCH_ROI(0, 64); }
+#undef JDET_LAUNCH_ROI
   } else {
     const int ch_per_cta = 32;
     const size_t smem = (size_t)kMaxSamples * sizeof(SampleTap);
