@@ -7,15 +7,16 @@
 //
 // B200 design (no offsets tensor, no columns tensor):
 //   D[pixel, co] = sum_k A[pixel, k] * Wt[co, k],  k = tap*C + c  (tap-major K; weights re-packed once)
-//   M tile = 128 output pixels, N = Co (<= 256, the whole output-channel extent), K block = 32.
+//   M tile = 128 output pixels, N = Co (<= 256, the whole output-channel extent), K block = 16,
+//   4 smem stages of 48 KB (the A producer is L2-latency-bound: depth, not width, hides it).
 //   A operand  : produced in-kernel.  8 producer warps derive the 9 sampling points of each pixel
 //                straight from its refined anchor (same fp32 op order as get_offset + im2col), gather
-//                the 4 bilinear corners from a channel-last copy of x with 16-B loads (8 lanes = 32
-//                channels = one 128-B row), interpolate in fp32, split each value into two TF32 terms
+//                the 4 bilinear corners from a channel-last copy of x with 16-B loads (4 lanes = 16
+//                channels = one 64-B row), interpolate in fp32, split each value into two TF32 terms
 //                (hi = top 19 bits, lo = exact remainder) and write both into shared memory directly in
-//                the UMMA canonical K-major SWIZZLE_128B layout.
+//                the UMMA canonical K-major SWIZZLE_64B layout.
 //   B operand  : weights pre-split into hi/lo and pre-swizzled in global memory, one contiguous
-//                Co x 128 B block per K block -> a single cp.async.bulk (TMA engine, UBLKCP) per term.
+//                Co x 64 B block per K block -> a single cp.async.bulk (TMA engine, UBLKCP) per term.
 //   MMA        : one elected thread issues tcgen05.mma.kind::tf32 128 x Co x 8; 3 products per K step
 //                (hi*hi + hi*lo + lo*hi  == "3xTF32", ~2^-21 relative error, fp32-class like the
 //                reference's SGEMM); accumulators live in TMEM, double-buffered (2 x Co columns) so the
@@ -27,7 +28,7 @@
 //                TMEM accumulator stage).
 //
 // Layout in HBM: x (N,C,H,W) fp32 -> channel-last scratch (N,H,W,C); anchors (N,H,W,5); weight
-// (Co,C,3,3) -> scratch [9*C/32][Co][32] hi and lo (swizzled); out (N,Co,H,W).
+// (Co,C,3,3) -> scratch [9*C/16][Co][16] hi and lo (swizzled); out (N,Co,H,W).
 #include "common.cuh"
 
 namespace jdet {
@@ -36,14 +37,17 @@ void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cuda
 
 namespace tc {
 
-constexpr int kProdWarps = 16;                // A-producer warps (4 pixels x 8 channel-quad lanes per warp step)
-constexpr int kPix = 128 / (kProdWarps * 4);  // pixels per lane per stage
+constexpr int kBlockK = 16;                   // fp32 elements per K block = one 64-B swizzle row
+constexpr int kRowBytes = kBlockK * 4;        // 64
+constexpr int kQuads = kBlockK / 4;           // lanes (channel quads) per pixel
+constexpr int kPixPerStep = 32 / kQuads;      // pixels a warp covers per step
+constexpr int kProdWarps = 16;                // A-producer warps
+constexpr int kPix = 128 / (kProdWarps * kPixPerStep);  // pixels per lane per stage
 constexpr int kMmaWarp = 4 + kProdWarps, kLoadWarp = 5 + kProdWarps;
 constexpr int kThreads = (6 + kProdWarps) * 32;
-constexpr int kStages = 2;
+constexpr int kStages = 4;
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 32;                 // fp32 elements = one 128-B swizzle row
-constexpr int kABytes = kBlockM * 128;      // 16 KB per term
+constexpr int kABytes = kBlockM * kRowBytes;   // 8 KB per term
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -86,16 +90,18 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-// K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+// K-major, SWIZZLE_64B (64-B rows), 8-row groups 512 B apart (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
   d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset
+  d |= (uint64_t)((8 * kRowBytes) >> 4) << 32;   // stride byte offset: one 8-row swizzle atom
   d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  d |= (uint64_t)4 << 61;                    // SWIZZLE_64B
   return d;
 }
+// 16-B chunk j of row r lives at chunk (j ^ ((r >> 1) & 3))  (Swizzle<2,4,3> on byte addresses)
+__device__ __host__ __forceinline__ int swz_chunk(int r, int j) { return j ^ ((r >> 1) & 3); }
 
 struct Params {
   const float* x_nhwc;      // (N, H, W, C)
@@ -108,7 +114,7 @@ struct Params {
   int num_tiles;
 };
 
-// weight (Co, C, 3, 3) -> hi/lo [kb][co][32] with kb = tap*(C/32) + c/32, 16-B chunks XOR-swizzled by (co & 7)
+// weight (Co, C, 3, 3) -> hi/lo [kb][co][16] with kb = tap*(C/16) + c/16, 16-B chunks swizzled like the smem rows
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, int Co, int C, float* __restrict__ hi,
                                                            float* __restrict__ lo) {
   const long long total = (long long)Co * C * 9;
@@ -120,9 +126,9 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
   const float v = w[i];
   const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
   const float l = v - h;                                      // exact
-  const int kb = t * (C / 32) + c / 32, e = c % 32;
-  const int chunk = (e >> 2) ^ (co & 7);
-  const size_t dst = ((size_t)kb * Co + co) * 32 + chunk * 4 + (e & 3);
+  const int kb = t * (C / kBlockK) + c / kBlockK, e = c % kBlockK;
+  const int chunk = swz_chunk(co, e >> 2);
+  const size_t dst = ((size_t)kb * Co + co) * kBlockK + chunk * 4 + (e & 3);
   hi[dst] = h;
   lo[dst] = l;
 }
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
 __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_bytes = p.Co * 128;
+  const int b_bytes = p.Co * kRowBytes;
   const int stage_bytes = 2 * kABytes + 2 * b_bytes;
   auto a_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return smem + (size_t)s * stage_bytes + kABytes; };
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HW = p.H * p.W;
   const long long P = (long long)p.N * HW;
-  const int cblocks = p.C / 32;
+  const int cblocks = p.C / kBlockK;
   const int num_kb = 9 * cblocks;
 
   if (warp == kLoadWarp && lane == 0) {
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
 
   if (warp >= 4 && warp < 4 + kProdWarps) {
     // =============================== A producers ==============================================
-    const int pw = warp - 4, sp = lane >> 3, q = lane & 7;
+    const int pw = warp - 4, sp = lane / kQuads, q = lane % kQuads;
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       // per-pixel anchor geometry (s2anet_head.py:689-698), 8 pixels per lane
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
       long long pbase[kPix];          // n * HW (pixel index of the image origin), -1 => row beyond the tensor
 #pragma unroll
       for (int it = 0; it < kPix; it++) {
-        const int r = pw * (4 * kPix) + it * 4 + sp;
+        const int r = pw * (kPixPerStep * kPix) + it * kPixPerStep + sp;
         const long long pix = (long long)tile * kBlockM + r;
         if (pix < P) {
           const int n = (int)(pix / HW), hw = (int)(pix - (long long)n * HW);
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 a = z, b = z, c = z, d = z;
             if (pbase[it] >= 0) {
-              const float* base = p.x_nhwc + (size_t)cb * 32 + q * 4;
+              const float* base = p.x_nhwc + (size_t)cb * kBlockK + q * 4;
               const size_t pb = (size_t)pbase[it];
               if (o00[it] >= 0) a = __ldg(reinterpret_cast<const float4*>(base + (pb + o00[it]) * p.C));
               if (o01[it] >= 0) b = __ldg(reinterpret_cast<const float4*>(base + (pb + o01[it]) * p.C));
@@ -246,8 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
           }
 #pragma unroll
           for (int it = 0; it < kPix; it++) {
-            const int r = pw * (4 * kPix) + it * 4 + sp;
-            const uint32_t off = (uint32_t)r * 128u + (uint32_t)((q ^ (r & 7)) << 4);
+            const int r = pw * (kPixPerStep * kPix) + it * kPixPerStep + sp;
+            const uint32_t off = (uint32_t)r * (uint32_t)kRowBytes + (uint32_t)(swz_chunk(r, q) << 4);
             float4 h4, l4;
             h4.x = __uint_as_float(__float_as_uint(v[it].x) & 0xffffe000u); l4.x = v[it].x - h4.x;
             h4.y = __uint_as_float(__float_as_uint(v[it].y) & 0xffffe000u); l4.y = v[it].y - h4.y;
@@ -271,8 +277,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], 2u * (uint32_t)b_bytes);
-          bulk_g2s(b_hi(stage), p.b_hi + (size_t)kb * p.Co * 32, (uint32_t)b_bytes, &full[stage]);
-          bulk_g2s(b_lo(stage), p.b_lo + (size_t)kb * p.Co * 32, (uint32_t)b_bytes, &full[stage]);
+          bulk_g2s(b_hi(stage), p.b_hi + (size_t)kb * p.Co * kBlockK, (uint32_t)b_bytes, &full[stage]);
+          bulk_g2s(b_lo(stage), p.b_lo + (size_t)kb * p.Co * kBlockK, (uint32_t)b_bytes, &full[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
 
 }  // namespace tc
 
-bool align_conv_tc_supported(int C, int Co) { return C % 32 == 0 && Co % 32 == 0 && Co >= 32 && Co <= 256; }
+bool align_conv_tc_supported(int C, int Co) { return C % tc::kBlockK == 0 && Co % 32 == 0 && Co >= 32 && Co <= 256; }
 
 size_t align_conv_tc_workspace_bytes(int N, int C, int H, int W, int Co) {
   return jdet_align_up((size_t)N * C * H * W * 4, 1024) + 2 * jdet_align_up((size_t)Co * C * 9 * 4, 1024);
@@ -372,7 +378,7 @@ int align_conv_tc_launch(const float* x, const float* anchors, const float* weig
   Params p{x_nhwc, anchors, b_hi, b_lo, out, N, C, H, W, Co, stride, 0};
   const long long P = (long long)N * H * W;
   p.num_tiles = (int)((P + kBlockM - 1) / kBlockM);
-  const size_t smem = 1024 + (size_t)kStages * (2 * kABytes + 2 * (size_t)Co * 128) + 256;
+  const size_t smem = 1024 + (size_t)kStages * (2 * kABytes + 2 * (size_t)Co * kRowBytes) + 256;
   cudaError_t e = cudaFuncSetAttribute(align_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
