@@ -65,11 +65,24 @@ int jdet_roi_align_rotated(int version, const float* input, int B, int C, int H,
                            int R, int PH, int PW, float spatial_scale, int sampling_ratio, float* output,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* backward w.r.t. input — replaces: _RotatedROIAlign[_v1].grad ops/roi_align_rotated_v1.py:328-351 (kernel :192-298),
+ * ops/roi_align_rotated.py:285-308 (kernel :164-255).  grad_output (R,C,PH,PW) -> grad_input (B,C,H,W), fully written. */
+size_t jdet_roi_align_rotated_backward_workspace_bytes(int B, int C, int H, int W, int R, int PH, int PW,
+                                                       int sampling_ratio);
+int jdet_roi_align_rotated_backward(int version, const float* grad_output, const float* rois, int R, int B, int C,
+                                    int H, int W, int PH, int PW, float spatial_scale, int sampling_ratio,
+                                    float* grad_input, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- feature_refine (rotated_feature_align) --------------------------------------------------
  * replaces: feature_refine_forward ops/fr.py:234-240 (kernel :114-165), FeatureRefineFunction.execute :257-264
  * features (N,C,H,W); best_rbboxes (N,H,W,5); output (N,C,H,W); points: 1 | 5.                     */
 int jdet_feature_refine(const float* features, const float* best_rbboxes, int N, int C, int H, int W,
                         int points, float spatial_scale, float* output, void* stream);
+
+/* backward w.r.t. features — replaces: FeatureRefineFunction.grad / feature_refine_backward ops/fr.py:242-252,266-271
+ * (kernel :167-232).  grad_output (N,C,H,W) -> grad_input (N,C,H,W), fully written. */
+int jdet_feature_refine_backward(const float* grad_output, const float* best_rbboxes, int N, int C, int H, int W,
+                                 int points, float spatial_scale, float* grad_input, void* stream);
 
 /* ---- AlignConv / DeformConv v1 forward -------------------------------------------------------
  * replaces: AlignConv.get_offset models/roi_heads/s2anet_head.py:677-713 (batched over images :716-721)
@@ -89,7 +102,7 @@ int jdet_deform_conv_forward(const float* x, const float* offset, const float* w
 /* replaces: AlignConv.execute models/roi_heads/s2anet_head.py:715-723 as ONE fused call:
  * offsets from anchors -> deformable 3x3 sampling -> tcgen05 GEMM (3xTF32 split, fp32-class
  * accuracy) -> ReLU.  x (N,C,H,W); anchors (N,H,W,5); weight (Co,C,3,3); out (N,Co,H,W).
- * Requires C % 32 == 0, Co % 16 == 0, Co <= 256.                                                    */
+ * tcgen05 path: C % 16 == 0, Co % 32 == 0, Co <= 256; other shapes compose offset + generic deform conv. */
 size_t jdet_align_conv_forward_workspace_bytes(int N, int C, int H, int W, int Co);
 int jdet_align_conv_forward(const float* x, const float* anchors, const float* weight, int N, int C, int H,
                             int W, int Co, float stride, float* out, void* workspace, size_t workspace_bytes,

@@ -118,6 +118,51 @@ __global__ void __launch_bounds__(256) feature_refine_p1_vec4_kernel(const float
   }
 }
 
+// backward (fr.py:167-232): grad_in = grad_out + scatter(grad_out * w) — thread = pixel, channel walk.
+// grad_in must already hold a copy of grad_out (the identity term); taps are float atomics as in the reference.
+template <int POINTS>
+__global__ void __launch_bounds__(256, 2) feature_refine_bwd_kernel(const float* __restrict__ grad_out,
+                                                                     const float* __restrict__ boxes, int C, int H, int W,
+                                                                     float spatial_scale, int ch_per_cta,
+                                                                     float* __restrict__ grad_in) {
+  const int HW = H * W;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
+  if (p >= HW) return;
+  const float* bb = boxes + ((size_t)n * HW + p) * 5;
+  const float roi_y = __fmul_rn(bb[0], spatial_scale), roi_x = __fmul_rn(bb[1], spatial_scale);
+  Tap4 taps[POINTS];
+  taps[0] = fr_tap(roi_y, roi_x, H, W);
+  if (POINTS > 1) {
+    const float rw = __fmul_rn(bb[2], spatial_scale), rh = __fmul_rn(bb[3], spatial_scale), ra = bb[4];
+    const float w2 = rw * 0.5f, h2 = rh * 0.5f;
+    const float ca = cosf(ra), sa = sinf(ra);
+    const float wx = __fmul_rn(ca, w2), wy = __fmul_rn(sa, w2), hx = __fmul_rn(-sa, h2), hy = __fmul_rn(ca, h2);
+    taps[1 % POINTS] = fr_tap(__fadd_rn(__fadd_rn(roi_y, wy), hy), __fadd_rn(__fadd_rn(roi_x, wx), hx), H, W);
+    taps[2 % POINTS] = fr_tap(__fadd_rn(__fsub_rn(roi_y, wy), hy), __fadd_rn(__fsub_rn(roi_x, wx), hx), H, W);
+    taps[3 % POINTS] = fr_tap(__fsub_rn(__fsub_rn(roi_y, wy), hy), __fsub_rn(__fsub_rn(roi_x, wx), hx), H, W);
+    taps[4 % POINTS] = fr_tap(__fsub_rn(__fadd_rn(roi_y, wy), hy), __fsub_rn(__fadd_rn(roi_x, wx), hx), H, W);
+  }
+  const float* src = grad_out + ((size_t)n * C + c0) * HW + p;
+  float* plane = grad_in + ((size_t)n * C + c0) * HW;
+  for (int c = c0; c < c1; c++) {
+    const float g = __ldg(src);
+#pragma unroll
+    for (int i = 0; i < POINTS; i++) {
+      const Tap4& t = taps[i];
+      if (t.o00 >= 0) {
+        atomicAdd(plane + t.o00, g * t.w1);
+        atomicAdd(plane + t.o01, g * t.w2);
+        atomicAdd(plane + t.o10, g * t.w3);
+        atomicAdd(plane + t.o11, g * t.w4);
+      }
+    }
+    src += HW;
+    plane += HW;
+  }
+}
+
 }  // namespace jdet
 
 // jdet.ops.fr.feature_refine(features, best_rbboxes, spatial_scale, points) (ops/fr.py:255-273)
@@ -144,5 +189,25 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
     feature_refine_p1_vec4_kernel<<<vgrid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, cpc, output);
   } else if (points == 1) feature_refine_kernel<1><<<grid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, output);
   else             feature_refine_kernel<5><<<grid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, output);
+  return (int)cudaGetLastError();
+}
+
+// backward of jdet_feature_refine w.r.t. features: FeatureRefineFunction.grad (ops/fr.py:266-271, 242-252)
+JDET_API int jdet_feature_refine_backward(const float* grad_output, const float* best_rbboxes, int N, int C, int H, int W,
+                                          int points, float spatial_scale, float* grad_input, void* stream) {
+  using namespace jdet;
+  if (N < 0 || C < 0 || H < 0 || W < 0 || (points != 1 && points != 5)) return JDET_ERR_BAD_ARG;
+  const size_t total = (size_t)N * C * H * W;
+  if (total == 0) return 0;
+  if (!grad_output || !best_rbboxes || !grad_input || N > 65535) return JDET_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  JDET_RETURN_IF_CUDA(cudaMemcpyAsync(grad_input, grad_output, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int HW = H * W;
+  const int ptiles = jdet_ceil_div(HW, 256);
+  int ch_per_cta = C;
+  while (ch_per_cta > 16 && (long long)ptiles * jdet_ceil_div(C, ch_per_cta) * N < 148 * 8) ch_per_cta = (ch_per_cta + 1) / 2;
+  dim3 grid(ptiles, jdet_ceil_div(C, ch_per_cta), N);
+  if (points == 1) feature_refine_bwd_kernel<1><<<grid, 256, 0, st>>>(grad_output, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, grad_input);
+  else             feature_refine_bwd_kernel<5><<<grid, 256, 0, st>>>(grad_output, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, grad_input);
   return (int)cudaGetLastError();
 }

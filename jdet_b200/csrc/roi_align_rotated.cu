@@ -217,6 +217,97 @@ __global__ void __launch_bounds__(256) roi_align_nchw_kernel(const float* __rest
   }
 }
 
+// ---- backward ------------------------------------------------------------------------------------
+// Replaces ROIAlignBackward (roi_align_rotated_v1.py:192-298 / roi_align_rotated.py:164-255):
+// grad_input[b,c,tap] += grad_out[r,c,bin] * w / (gh*gw).  Same per-RoI sample table as the forward.
+//   staged: gradients are accumulated in a channel-last scratch with 16-B vector atomics
+//           (red.global.add.v4.f32: one L2 atomic per 4 channels instead of 4), then re-laid to NCHW;
+//   direct: scalar atomics into the NCHW gradient (few RoIs / odd channel counts).
+// Float atomics make the last bits order-dependent, exactly as in the reference.
+template <int VERSION, int SLAB>
+__global__ void __launch_bounds__(256) roi_align_bwd_nhwc_kernel(const float* __restrict__ grad_out,
+                                                                  const float* __restrict__ rois, int C, int H, int W,
+                                                                  int PH, int PW, float spatial_scale, int sample_num,
+                                                                  float* __restrict__ grad_nhwc) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int nbins = PH * PW;
+  const int r = blockIdx.x, c0 = blockIdx.y * SLAB;
+  constexpr int QL = SLAB / 4;
+  __shared__ RoiGeom g;
+  if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)r * 6, spatial_scale, sample_num, PH, PW);
+  __syncthreads();
+  const int spb = g.gh * g.gw;
+  SampleTap* taps = reinterpret_cast<SampleTap*>(smem);
+  float* s_go = reinterpret_cast<float*>(taps + nbins * spb);   // [SLAB][nbins], as laid out in grad_out
+  for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
+    const int bin = s / spb, k = s - bin * spb;
+    taps[s] = make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
+  }
+  const float* src = grad_out + ((size_t)r * C + c0) * nbins;
+  for (int i = threadIdx.x; i < SLAB * nbins; i += blockDim.x) s_go[i] = __ldg(src + i);
+  __syncthreads();
+  float* base = grad_nhwc + (size_t)g.batch * H * W * C + c0;
+  const int q = threadIdx.x % QL;
+  const float cnt = (float)spb;                      // the backward divides by gh*gw in both versions
+  for (int bin = threadIdx.x / QL; bin < nbins; bin += blockDim.x / QL) {
+    const float4 go = make_float4(s_go[(4 * q + 0) * nbins + bin], s_go[(4 * q + 1) * nbins + bin],
+                                  s_go[(4 * q + 2) * nbins + bin], s_go[(4 * q + 3) * nbins + bin]);
+    const SampleTap* tp = taps + bin * spb;
+    for (int k = 0; k < spb; k++) {
+      const SampleTap t = tp[k];
+      if (t.o00 < 0) continue;
+      const int o[4] = {t.o00, t.o01, t.o10, t.o11};
+      const float w[4] = {t.w1, t.w2, t.w3, t.w4};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float4 v = make_float4(go.x * w[j] / cnt, go.y * w[j] / cnt, go.z * w[j] / cnt, go.w * w[j] / cnt);
+        atomicAdd(reinterpret_cast<float4*>(base + (size_t)o[j] * C) + q, v);
+      }
+    }
+  }
+}
+
+template <int VERSION>
+__global__ void __launch_bounds__(256) roi_align_bwd_nchw_kernel(const float* __restrict__ grad_out,
+                                                                  const float* __restrict__ rois, int C, int H, int W,
+                                                                  int PH, int PW, float spatial_scale, int sample_num,
+                                                                  int ch_per_cta, float* __restrict__ grad_in) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int nbins = PH * PW;
+  const int r = blockIdx.x, c0 = blockIdx.y * ch_per_cta;
+  const int c1 = min(C, c0 + ch_per_cta);
+  __shared__ RoiGeom g;
+  if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)r * 6, spatial_scale, sample_num, PH, PW);
+  __syncthreads();
+  const int spb = g.gh * g.gw;
+  const bool tabled = (long long)nbins * spb <= kMaxSamples;
+  SampleTap* taps = reinterpret_cast<SampleTap*>(smem);
+  if (tabled) {
+    for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
+      const int bin = s / spb, k = s - bin * spb;
+      taps[s] = make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
+    }
+    __syncthreads();
+  }
+  const size_t plane = (size_t)H * W;
+  float* gb = grad_in + (size_t)g.batch * C * plane;
+  const float cnt = (float)spb;
+  const int total = (c1 - c0) * nbins;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c = c0 + i / nbins, bin = i % nbins;
+    float* p = gb + (size_t)c * plane;
+    const float go = __ldg(grad_out + ((size_t)r * C + c) * nbins + bin);
+    for (int k = 0; k < spb; k++) {
+      const SampleTap t = tabled ? taps[bin * spb + k] : make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
+      if (t.o00 < 0) continue;
+      atomicAdd(p + t.o00, go * t.w1 / cnt);
+      atomicAdd(p + t.o01, go * t.w2 / cnt);
+      atomicAdd(p + t.o10, go * t.w3 / cnt);
+      atomicAdd(p + t.o11, go * t.w4 / cnt);
+    }
+  }
+}
+
 static bool use_staged(int B, int C, int H, int W, int R, int PH, int PW, int sample_num) {
   if (sample_num <= 0 || C % 64 != 0) return false;
   if ((long long)PH * PW * sample_num * sample_num > kMaxSamples) return false;
@@ -273,6 +364,55 @@ JDET_API int jdet_roi_align_rotated(int version, const float* input, int B, int 
       roi_align_nchw_kernel<1><<<grid, 256, smem, st>>>(input, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, ch_per_cta, output);
     else
       roi_align_nchw_kernel<0><<<grid, 256, smem, st>>>(input, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, ch_per_cta, output);
+  }
+  return (int)cudaGetLastError();
+}
+
+// backward of jdet_roi_align_rotated w.r.t. input: _RotatedROIAlign[_v1].grad (roi_align_rotated_v1.py:328-351,
+// roi_align_rotated.py:285-308).  grad_output (R,C,PH,PW) -> grad_input (B,C,H,W), written in full.
+JDET_API size_t jdet_roi_align_rotated_backward_workspace_bytes(int B, int C, int H, int W, int R, int PH, int PW,
+                                                                int sampling_ratio) {
+  return jdet_roi_align_rotated_workspace_bytes(B, C, H, W, R, PH, PW, sampling_ratio);
+}
+
+JDET_API int jdet_roi_align_rotated_backward(int version, const float* grad_output, const float* rois, int R, int B, int C,
+                                             int H, int W, int PH, int PW, float spatial_scale, int sampling_ratio,
+                                             float* grad_input, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace jdet;
+  if ((version != 0 && version != 1) || B < 0 || C < 0 || H < 0 || W < 0 || R < 0 || PH <= 0 || PW <= 0)
+    return JDET_ERR_BAD_ARG;
+  const size_t in_bytes = (size_t)B * C * H * W * sizeof(float);
+  if (in_bytes == 0) return 0;
+  if (!grad_input || (R > 0 && (!grad_output || !rois))) return JDET_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nbins = PH * PW;
+  if (R == 0) { JDET_RETURN_IF_CUDA(cudaMemsetAsync(grad_input, 0, in_bytes, st)); return 0; }
+  if (use_staged(B, C, H, W, R, PH, PW, sampling_ratio)) {
+    if (!workspace || workspace_bytes < jdet_align_up(in_bytes, 256)) return JDET_ERR_WORKSPACE;
+    float* nhwc = (float*)workspace;
+    JDET_RETURN_IF_CUDA(cudaMemsetAsync(nhwc, 0, in_bytes, st));
+    const int slab = (C % 128 == 0) ? 128 : 64;
+    const size_t smem = (size_t)nbins * sampling_ratio * sampling_ratio * sizeof(SampleTap) + (size_t)slab * nbins * 4;
+    dim3 grid(R, C / slab);
+#define JDET_LAUNCH_BWD(V, S)                                                                                          \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024)                                                                                              \
+      JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_bwd_nhwc_kernel<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    roi_align_bwd_nhwc_kernel<V, S><<<grid, 256, smem, st>>>(grad_output, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, nhwc);   \
+  } while (0)
+    if (version == 1) { if (slab == 128) JDET_LAUNCH_BWD(1, 128); else JDET_LAUNCH_BWD(1, 64); }
+    else              { if (slab == 128) JDET_LAUNCH_BWD(0, 128); else JDET_LAUNCH_BWD(0, 64); }
+#undef JDET_LAUNCH_BWD
+    launch_nchw_to_nhwc(nhwc, grad_input, B, H * W, C, st);   // (B, HW, C) -> (B, C, HW): same tiled transpose, roles swapped
+  } else {
+    JDET_RETURN_IF_CUDA(cudaMemsetAsync(grad_input, 0, in_bytes, st));
+    const int ch_per_cta = 32;
+    const size_t smem = (size_t)kMaxSamples * sizeof(SampleTap);
+    dim3 grid(R, jdet_ceil_div(C, ch_per_cta));
+    if (version == 1)
+      roi_align_bwd_nchw_kernel<1><<<grid, 256, smem, st>>>(grad_output, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, ch_per_cta, grad_input);
+    else
+      roi_align_bwd_nchw_kernel<0><<<grid, 256, smem, st>>>(grad_output, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, ch_per_cta, grad_input);
   }
   return (int)cudaGetLastError();
 }

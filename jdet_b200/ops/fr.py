@@ -1,7 +1,7 @@
 """jdet.ops.fr mirror — feature_refine / FR / FeatureRefineModule (reference: python/jdet/ops/fr.py:255-347).
 
 feature_refine is R3Det's rotated feature alignment: out = in + sum_i bilinear(in, point_i), the points
-being the box centre (points=1) or centre + 4 corners (points=5).  Forward only.
+being the box centre (points=1) or centre + 4 corners (points=5).  Forward and backward (grad w.r.t. features).
 """
 import torch
 from torch import nn
@@ -9,7 +9,7 @@ from torch import nn
 from ._common import check, f32c, lib, require_cuda, stream_ptr
 
 
-def feature_refine(features, best_rbboxes, spatial_scale, points=1):
+def _feature_refine_fwd(features, best_rbboxes, spatial_scale, points):
     assert points in [1, 5]                                    # fr.py:261
     require_cuda(features, best_rbboxes)
     x, b = f32c(features), f32c(best_rbboxes)
@@ -22,6 +22,39 @@ def feature_refine(features, best_rbboxes, spatial_scale, points=1):
         check(lib().jdet_feature_refine(x.data_ptr(), b.data_ptr(), N, C, H, W, points, float(spatial_scale),
                                         out.data_ptr(), stream_ptr(x.device)), "feature_refine")
     return out
+
+
+def _feature_refine_bwd(grad_output, best_rbboxes, spatial_scale, points):
+    g, b = f32c(grad_output), f32c(best_rbboxes)
+    N, C, H, W = g.shape
+    gi = torch.empty_like(g)
+    if gi.numel() == 0:
+        return gi
+    with torch.cuda.device(g.device):
+        check(lib().jdet_feature_refine_backward(g.data_ptr(), b.data_ptr(), N, C, H, W, points, float(spatial_scale),
+                                                 gi.data_ptr(), stream_ptr(g.device)), "feature_refine_backward")
+    return gi
+
+
+class FeatureRefineFunction(torch.autograd.Function):
+    """fr.py:255-271 (execute/grad -> forward/backward); boxes get no gradient, as in the reference."""
+
+    @staticmethod
+    def forward(ctx, features, best_rbboxes, spatial_scale, points=1):
+        ctx.spatial_scale, ctx.points = spatial_scale, points
+        ctx.save_for_backward(best_rbboxes)
+        return _feature_refine_fwd(features, best_rbboxes, spatial_scale, points)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (boxes,) = ctx.saved_tensors
+        return _feature_refine_bwd(grad_output, boxes, ctx.spatial_scale, ctx.points), None, None, None
+
+
+def feature_refine(features, best_rbboxes, spatial_scale, points=1):
+    if torch.is_grad_enabled() and isinstance(features, torch.Tensor) and features.requires_grad:
+        return FeatureRefineFunction.apply(features, best_rbboxes, spatial_scale, points)
+    return _feature_refine_fwd(features, best_rbboxes, spatial_scale, points)
 
 
 class FR(nn.Module):

@@ -5,11 +5,11 @@ count = grid_h*grid_w.  (The reference module also re-exports RiRoIAlign, which 
 """
 from torch import nn
 
-from .roi_align_rotated_v1 import _pair, _roi_align_impl
+from .roi_align_rotated_v1 import _pair, _roi_align_dispatch
 
 
 def roi_align(input, rois, output_size, spatial_scale, sampling_ratio):
-    return _roi_align_impl(0, input, rois, output_size, spatial_scale, sampling_ratio)
+    return _roi_align_dispatch(0, input, rois, output_size, spatial_scale, sampling_ratio)
 
 
 class ROIAlignRotated(nn.Module):

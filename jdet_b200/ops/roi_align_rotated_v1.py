@@ -1,7 +1,7 @@
 """jdet.ops.roi_align_rotated_v1 mirror (reference: python/jdet/ops/roi_align_rotated_v1.py:300-365).
 
 v1 convention (used by OrientedSingleRoIExtractor / Oriented R-CNN): centre shifted by -0.5,
-x = xx*cos + yy*sin, clamp on `< 0`, count = max(grid, 1).  Forward only (backward: later round).
+x = xx*cos + yy*sin, clamp on `< 0`, count = max(grid, 1).  Forward and backward (grad w.r.t. input).
 """
 import torch
 from torch import nn
@@ -34,9 +34,51 @@ def _roi_align_impl(version, input, rois, output_size, spatial_scale, sampling_r
     return out
 
 
+def _roi_align_backward_impl(version, grad_output, rois, input_shape, output_size, spatial_scale, sampling_ratio):
+    g, r = f32c(grad_output), f32c(rois)
+    ph, pw = _pair(output_size)
+    B, C, H, W = input_shape
+    R = r.shape[0]
+    grad_in = torch.empty((B, C, H, W), dtype=torch.float32, device=g.device)
+    if grad_in.numel() == 0:
+        return grad_in
+    sr = int(sampling_ratio)
+    L = lib()
+    with torch.cuda.device(g.device):
+        ws = scratch(L.jdet_roi_align_rotated_backward_workspace_bytes(B, C, H, W, R, ph, pw, sr), g.device)
+        check(L.jdet_roi_align_rotated_backward(version, g.data_ptr(), r.data_ptr(), R, B, C, H, W, ph, pw,
+                                                float(spatial_scale), sr, grad_in.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                stream_ptr(g.device)), "roi_align_rotated_backward")
+    return grad_in
+
+
+class _RotatedROIAlignFn(torch.autograd.Function):
+    """jt.Function mirror (execute/grad -> forward/backward); rois get no gradient, as in the reference."""
+
+    @staticmethod
+    def forward(ctx, version, input, rois, output_size, spatial_scale, sampling_ratio):
+        ctx.version, ctx.output_size, ctx.spatial_scale, ctx.sampling_ratio = version, output_size, spatial_scale, sampling_ratio
+        ctx.input_shape = tuple(input.shape)
+        ctx.save_for_backward(rois)
+        return _roi_align_impl(version, input, rois, output_size, spatial_scale, sampling_ratio)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (rois,) = ctx.saved_tensors
+        gi = _roi_align_backward_impl(ctx.version, grad_output, rois, ctx.input_shape, ctx.output_size,
+                                      ctx.spatial_scale, ctx.sampling_ratio)
+        return None, gi, None, None, None, None
+
+
+def _roi_align_dispatch(version, input, rois, output_size, spatial_scale, sampling_ratio):
+    if torch.is_grad_enabled() and isinstance(input, torch.Tensor) and input.requires_grad:
+        return _RotatedROIAlignFn.apply(version, input, rois, output_size, spatial_scale, sampling_ratio)
+    return _roi_align_impl(version, input, rois, output_size, spatial_scale, sampling_ratio)
+
+
 def roi_align(input, rois, output_size, spatial_scale, sampling_ratio):
     """_RotatedROIAlign_v1.apply: input (B,C,H,W), rois (R,6)=[batch,cx,cy,w,h,theta] -> (R,C,PH,PW)."""
-    return _roi_align_impl(1, input, rois, output_size, spatial_scale, sampling_ratio)
+    return _roi_align_dispatch(1, input, rois, output_size, spatial_scale, sampling_ratio)
 
 
 class ROIAlignRotated_v1(nn.Module):

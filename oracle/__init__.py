@@ -188,6 +188,25 @@ def roi_align_rotated(input, rois, output_size, spatial_scale, sampling_ratio=0,
     return out
 
 
+def roi_align_rotated_backward(grad_out, rois, input_shape, spatial_scale, sampling_ratio=0, version=1):
+    g, r = _f32(grad_out), _f32(rois).reshape(-1, 6)
+    B, C, H, W = input_shape
+    R, _, ph, pw = g.shape
+    out = np.zeros((B, C, H, W), np.float32)
+    lib().orc_roi_align_rotated_backward(version, _p(g), _p(r), R, B, C, H, W, ph, pw,
+                                         ctypes.c_float(np.float32(spatial_scale)), int(sampling_ratio), _p(out))
+    return out
+
+
+def feature_refine_backward(grad_out, best_rbboxes, spatial_scale, points=1):
+    g = _f32(grad_out)
+    N, C, H, W = g.shape
+    b = _f32(best_rbboxes).reshape(N, H, W, 5)
+    out = np.zeros_like(g)
+    lib().orc_feature_refine_backward(_p(g), _p(b), N, C, H, W, points, ctypes.c_float(np.float32(spatial_scale)), _p(out))
+    return out
+
+
 def feature_refine(features, best_rbboxes, spatial_scale, points=1, threads=0):
     x = _f32(features)
     N, C, H, W = x.shape

@@ -256,6 +256,17 @@ static void launch(const float* input_p, const float* rois_p, int num_rois, int 
       output_size, input_p, rois_p, spatial_scale, sampling_ratio, channels, height, width,
       pooled_height, pooled_width, output_p);
 }}
+// backward launch: ops/roi_align_rotated*.py grad() (memset of grad_input, then ROIAlignBackward)
+static void launch_bwd(const float* grad_p, const float* rois_p, int num_rois, int batch, int channels, int height,
+                       int width, int pooled_height, int pooled_width, float spatial_scale,
+                       float sampling_ratio, float* grad_input_p, cudaStream_t st) {{
+  cudaMemsetAsync(grad_input_p, 0, (size_t)batch * channels * height * width * 4, st);
+  int output_size = num_rois * pooled_height * pooled_width * channels;
+  if (output_size == 0) return;
+  ROIAlignBackward<float><<<GET_BLOCKS(output_size), THREADS_PER_BLOCK, 0, st>>>(
+      output_size, grad_p, rois_p, spatial_scale, sampling_ratio, channels, height, width,
+      pooled_height, pooled_width, grad_input_p);
+}}
 }}  // namespace {ns}
 #undef CUDA_1D_KERNEL_LOOP
 #undef THREADS_PER_BLOCK
@@ -272,6 +283,15 @@ static void launch(const float* in0_p, const float* in1_p, int n, int c, int h, 
   const int output_size = n * c * h * w;
   if (output_size == 0) return;
   feature_refine_forward_kernel<float><<<GET_BLOCKS(output_size), THREADS_PER_BLOCK, 0, st>>>(
+      output_size, points, in0_p, in1_p, spatial_scale, c, h, w, out0_p);
+}}
+// backward: ops/fr.py:242-252 (zeros_like, then feature_refine_backward_kernel)
+static void launch_bwd(const float* in0_p, const float* in1_p, int n, int c, int h, int w, int points,
+                       float spatial_scale, float* out0_p, cudaStream_t st) {{
+  const int output_size = n * c * h * w;
+  if (output_size == 0) return;
+  cudaMemsetAsync(out0_p, 0, (size_t)output_size * 4, st);
+  feature_refine_backward_kernel<float><<<GET_BLOCKS(output_size), THREADS_PER_BLOCK, 0, st>>>(
       output_size, points, in0_p, in1_p, spatial_scale, c, h, w, out0_p);
 }}
 }}  // namespace ref_fr
@@ -328,6 +348,20 @@ int ref_roi_align_rotated_cuda(int version, const float* input, const float* roi
                                        spatial_scale, sampling_ratio, out, (cudaStream_t)st);
   else              ref_roi_v1::launch(input, rois, num_rois, channels, height, width, ph, pw,
                                        spatial_scale, sampling_ratio, out, (cudaStream_t)st);
+  return (int)cudaGetLastError();
+}
+int ref_roi_align_rotated_backward_cuda(int version, const float* grad, const float* rois, int num_rois, int batch,
+                                        int channels, int height, int width, int ph, int pw,
+                                        float spatial_scale, float sampling_ratio, float* grad_input, void* st) {
+  if (version == 0) ref_roi_v0::launch_bwd(grad, rois, num_rois, batch, channels, height, width, ph, pw,
+                                           spatial_scale, sampling_ratio, grad_input, (cudaStream_t)st);
+  else              ref_roi_v1::launch_bwd(grad, rois, num_rois, batch, channels, height, width, ph, pw,
+                                           spatial_scale, sampling_ratio, grad_input, (cudaStream_t)st);
+  return (int)cudaGetLastError();
+}
+int ref_feature_refine_backward_cuda(const float* grad, const float* boxes, int n, int c, int h, int w,
+                                     int points, float spatial_scale, float* grad_in, void* st) {
+  ref_fr::launch_bwd(grad, boxes, n, c, h, w, points, spatial_scale, grad_in, (cudaStream_t)st);
   return (int)cudaGetLastError();
 }
 int ref_feature_refine_cuda(const float* feat, const float* boxes, int n, int c, int h, int w,

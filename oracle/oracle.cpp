@@ -207,6 +207,22 @@ inline float bilinear_zeropad(const float* plane, int H, int W, float h, float w
   return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
 }
 
+// taps + weights of one sample, shared by forward/backward (bilinear_interpolate_gradient,
+// ops/roi_align_rotated_v1.py:148-190, ops/fr.py:69-112): returns false when the sample is out of range.
+inline bool tap_weights(int H, int W, float y, float x, int (&off)[4], float (&w)[4]) {
+  if (y < -1.0 || y > H || x < -1.0 || x > W) return false;
+  if (y <= 0) y = 0;
+  if (x <= 0) x = 0;
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+  const float ly = y - yl, lx = x - xl;
+  const float hy = (float)(1. - ly), hx = (float)(1. - lx);
+  off[0] = yl * W + xl; off[1] = yl * W + xh; off[2] = yh * W + xl; off[3] = yh * W + xh;
+  w[0] = hy * hx; w[1] = hy * lx; w[2] = ly * hx; w[3] = ly * lx;
+  return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -357,6 +373,84 @@ void orc_feature_refine(const float* feat, const float* boxes, int N, int C, int
           out[(((size_t)n * C + c) * H + h) * W + w] = v;
         }
       }
+}
+
+// ROIAlignBackward (ops/roi_align_rotated_v1.py:192-298, ops/roi_align_rotated.py:164-255):
+// grad_input[b,c,tap] += grad_out[n,c,ph,pw] * w / (gh*gw).  The reference scatters with float
+// atomicAdd (order-dependent rounding); this restatement accumulates in double.
+void orc_roi_align_rotated_backward(int version, const float* grad_out, const float* rois, int R, int B, int C, int H,
+                                    int W, int PH, int PW, float spatial_scale, int sample_num, float* grad_in) {
+  std::vector<double> acc((size_t)B * C * H * W, 0.0);
+  for (int n = 0; n < R; n++) {
+    const float* roi = rois + (size_t)n * 6;
+    const int batch = (int)roi[0];
+    float cw, ch;
+    if (version == 1) { cw = roi[1] * spatial_scale - 0.5f; ch = roi[2] * spatial_scale - 0.5f; }
+    else { cw = roi[1] * spatial_scale; ch = roi[2] * spatial_scale; }
+    float rw = roi[3] * spatial_scale, rh = roi[4] * spatial_scale;
+    const float theta = roi[5];
+    rw = std::max(rw, 1.f);
+    rh = std::max(rh, 1.f);
+    const float bin_h = rh / (float)PH, bin_w = rw / (float)PW;
+    const int gh = sample_num > 0 ? sample_num : (int)std::ceil(rh / PH);
+    const int gw = sample_num > 0 ? sample_num : (int)std::ceil(rw / PW);
+    const float start_h = (float)(-rh / 2.0), start_w = (float)(-rw / 2.0);
+    const float ct = std::cos(theta), st = std::sin(theta);
+    const float count = (float)(gh * gw);
+    for (int ph = 0; ph < PH; ph++)
+      for (int pw = 0; pw < PW; pw++)
+        for (int iy = 0; iy < gh; iy++) {
+          const float yy = start_h + ph * bin_h + (float)(iy + .5f) * bin_h / (float)gh;
+          for (int ix = 0; ix < gw; ix++) {
+            const float xx = start_w + pw * bin_w + (float)(ix + .5f) * bin_w / (float)gw;
+            float x, y;
+            if (version == 1) { x = xx * ct + yy * st + cw; y = yy * ct - xx * st + ch; }
+            else { x = xx * ct - yy * st + cw; y = xx * st + yy * ct + ch; }
+            int off[4]; float w[4];
+            if (!tap_weights(H, W, y, x, off, w)) continue;
+            for (int c = 0; c < C; c++) {
+              const float g = grad_out[(((size_t)n * C + c) * PH + ph) * PW + pw];
+              double* plane = acc.data() + ((size_t)batch * C + c) * H * W;
+              for (int k = 0; k < 4; k++) plane[off[k]] += (double)(g * w[k] / count);
+            }
+          }
+        }
+  }
+  for (size_t i = 0; i < acc.size(); i++) grad_in[i] = (float)acc[i];
+}
+
+// feature_refine_backward_kernel (ops/fr.py:167-232): grad_in = grad_out + scatter of grad_out * w.
+void orc_feature_refine_backward(const float* grad_out, const float* boxes, int N, int C, int H, int W, int points,
+                                 float spatial_scale, float* grad_in) {
+  std::vector<double> acc((size_t)N * C * H * W);
+  for (size_t i = 0; i < acc.size(); i++) acc[i] = grad_out[i];
+  for (int n = 0; n < N; n++)
+    for (int h = 0; h < H; h++)
+      for (int w = 0; w < W; w++) {
+        const float* bb = boxes + (((size_t)n * H + h) * W + w) * 5;
+        const float roi_y = bb[0] * spatial_scale, roi_x = bb[1] * spatial_scale;
+        float px[5] = {roi_x, 0, 0, 0, 0}, py[5] = {roi_y, 0, 0, 0, 0};
+        if (points > 1) {
+          const float rw = bb[2] * spatial_scale, rh = bb[3] * spatial_scale, ra = bb[4];
+          const float w2 = rw / 2, h2 = rh / 2;
+          const float ca = cosf(ra), sa = sinf(ra);
+          const float wx = ca * w2, wy = sa * w2, hx = -sa * h2, hy = ca * h2;
+          px[1] = roi_x + wx + hx; py[1] = roi_y + wy + hy;
+          px[2] = roi_x - wx + hx; py[2] = roi_y - wy + hy;
+          px[3] = roi_x - wx - hx; py[3] = roi_y - wy - hy;
+          px[4] = roi_x + wx - hx; py[4] = roi_y + wy - hy;
+        }
+        for (int i = 0; i < points; i++) {
+          int off[4]; float wt[4];
+          if (!tap_weights(H, W, py[i], px[i], off, wt)) continue;
+          for (int c = 0; c < C; c++) {
+            const float g = grad_out[(((size_t)n * C + c) * H + h) * W + w];
+            double* plane = acc.data() + ((size_t)n * C + c) * H * W;
+            for (int k = 0; k < 4; k++) plane[off[k]] += (double)(g * wt[k]);
+          }
+        }
+      }
+  for (size_t i = 0; i < acc.size(); i++) grad_in[i] = (float)acc[i];
 }
 
 // models/roi_heads/s2anet_head.py:677-713 — AlignConv.get_offset for ONE image, kernel_size k (odd).

@@ -55,6 +55,27 @@ def roi_align_rotated(x, rois, out_hw, scale, sr, version):
     return out
 
 
+def roi_align_rotated_backward(grad, rois, in_shape, scale, sr, version):
+    R = oracle.ref_cuda()
+    B, C, H, W = in_shape
+    ph, pw = grad.shape[2:]
+    out = torch.empty(in_shape, device="cuda")
+    assert R.ref_roi_align_rotated_backward_cuda(version, _p(grad), _p(rois), rois.shape[0], B, C, H, W, ph, pw,
+                                                 ctypes.c_float(np.float32(scale)), ctypes.c_float(float(sr)), _p(out), _st()) == 0
+    torch.cuda.synchronize()
+    return out
+
+
+def feature_refine_backward(grad, boxes, scale, points):
+    R = oracle.ref_cuda()
+    N, C, H, W = grad.shape
+    out = torch.empty_like(grad)
+    assert R.ref_feature_refine_backward_cuda(_p(grad), _p(boxes), N, C, H, W, points, ctypes.c_float(np.float32(scale)),
+                                              _p(out), _st()) == 0
+    torch.cuda.synchronize()
+    return out
+
+
 def feature_refine(x, boxes, scale, points):
     R = oracle.ref_cuda()
     N, C, H, W = x.shape

@@ -301,6 +301,58 @@ def test_feature_refine_module():
     assert [tuple(o.shape) for o in out] == [(2, 16, 16, 16), (2, 16, 8, 8)]
 
 
+# ------------------------------------------------------------------------------------ backward
+BWD_TOL = 2e-4   # float atomics: summation order differs from the fp64-accumulating oracle (and run to run)
+
+
+@pytest.mark.parametrize("version", [0, 1])
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, C=64, H=40, W=56, R=300, out=(7, 7), sr=2, scale=0.25),      # staged: channel-last scratch + vector atomics
+    dict(B=1, C=128, H=32, W=32, R=200, out=(5, 3), sr=3, scale=0.125),
+    dict(B=2, C=24, H=40, W=56, R=60, out=(7, 7), sr=2, scale=0.25),       # direct NCHW atomics
+    dict(B=1, C=16, H=48, W=48, R=30, out=(7, 7), sr=0, scale=0.25),       # adaptive grid
+])
+def test_roi_align_backward(version, cfg):
+    rng = np.random.default_rng(cfg["R"] + 10 * version)
+    x = rng.standard_normal((cfg["B"], cfg["C"], cfg["H"], cfg["W"])).astype(np.float32)
+    extent = cfg["W"] / cfg["scale"]
+    rois = _rois(rng, cfg["R"], cfg["B"], extent, 8, extent / 2)
+    rois[:3, 1:3] = [[-20, -20], [extent + 30, 5], [0, 0]]
+    go = rng.standard_normal((cfg["R"], cfg["C"]) + cfg["out"]).astype(np.float32)
+    mod = ops().roi_align_rotated_v1 if version == 1 else ops().roi_align_rotated
+    xt = cu(x).requires_grad_(True)
+    out = mod.roi_align(xt, cu(rois), cfg["out"], cfg["scale"], cfg["sr"])
+    out.backward(cu(go))
+    got = xt.grad.cpu().numpy()
+    want = oracle.roi_align_rotated_backward(go, rois, x.shape, cfg["scale"], cfg["sr"], version)
+    assert np.abs(got - want).max() <= BWD_TOL, np.abs(got - want).max()
+    if _refcuda.available():
+        ref = _refcuda.roi_align_rotated_backward(cu(go), cu(rois), x.shape, cfg["scale"], cfg["sr"], version).cpu().numpy()
+        assert np.abs(got - ref).max() <= BWD_TOL
+    # forward under autograd is the same forward
+    assert np.array_equal(out.detach().cpu().numpy(),
+                          mod.roi_align(cu(x), cu(rois), cfg["out"], cfg["scale"], cfg["sr"]).cpu().numpy())
+
+
+@pytest.mark.parametrize("points", [1, 5])
+def test_feature_refine_backward(points):
+    rng = np.random.default_rng(40 + points)
+    N, C, H, W, stride = 2, 24, 20, 28, 8.0
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    a = s2anet_anchors(rng, N, H, W, stride)
+    boxes = a[..., [1, 0, 2, 3, 4]].copy()
+    boxes[0, 0, :4, :2] = [[-50, -50]] * 4
+    go = rng.standard_normal(x.shape).astype(np.float32)
+    xt = cu(x).requires_grad_(True)
+    ops().fr.feature_refine(xt, cu(boxes), 1 / stride, points).backward(cu(go))
+    got = xt.grad.cpu().numpy()
+    want = oracle.feature_refine_backward(go, boxes, 1 / stride, points)
+    assert np.abs(got - want).max() <= BWD_TOL, np.abs(got - want).max()
+    if _refcuda.available():
+        ref = _refcuda.feature_refine_backward(cu(go), cu(boxes), 1 / stride, points).cpu().numpy()
+        assert np.abs(got - ref).max() <= BWD_TOL
+
+
 # ------------------------------------------------------------------------------------ DeformConv / AlignConv
 @pytest.mark.parametrize("cfg", [
     dict(B=2, C=16, H=12, W=14, Co=24, k=3, stride=1, pad=1, dil=1, groups=1, dg=1),
