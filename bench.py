@@ -318,6 +318,23 @@ def run_extra(torch, dist, ops, jdist, dev, rank, world, peaks, flush):
                          "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg}}
         del b1, b2
 
+    # roi_align_rotated backward at cfg2: grad_out (2048,256,7,7) -> grad_in (1,256,256,256)
+    from jdet_b200.ops.roi_align_rotated_v1 import _roi_align_backward_impl
+    rois_b = cu(np.concatenate([np.zeros((2048, 1), np.float32), dota_boxes(rng, 2048, 1024.0)], 1))
+    gbw = torch.Generator(device=dev).manual_seed(5 + rank)
+    go = torch.randn((2048, 256, 7, 7), device=dev, generator=gbw)
+    fn = lambda: _roi_align_backward_impl(1, go, rois_b, (1, 256, 256, 256), (7, 7), 0.25, 2)
+    fn()
+    K = 20
+    ms = agg(time_steps(torch, fn, K, 3, flush)) / K
+    alg = go.numel() * 4 + 256 * 256 * 256 * 4 + rois_b.numel() * 4
+    ex["roi_align_rotated_backward"] = {
+        "metric": "RoIs/s", "value": 2048 * world / (ms * 1e-3), "unit": "RoIs/s", "ms_per_step": ms, "steps": K,
+        "config": {"workload": "ROIAlignRotated_v1 backward w.r.t. input at cfg2 (channel-last scratch + 16-B vector atomics + relayout)"},
+        "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg}}
+    del go
+
     # cfg4: S2ANet-R50-FPN shapes, bs 8: feature_refine + AlignConv over the 5 levels
     levels = [(128, 8), (64, 16), (32, 32), (16, 64), (8, 128)]
     g = torch.Generator(device=dev).manual_seed(77 + rank)

@@ -1,1 +1,1 @@
-from .s2anet_head import AlignConv  # noqa: F401
+from .s2anet_head import AlignConv, bbox_decode  # noqa: F401

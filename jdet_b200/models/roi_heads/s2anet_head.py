@@ -8,6 +8,16 @@ from torch import nn
 
 from ...ops._common import check, f32c, lib, require_cuda, scratch, stream_ptr
 from ...ops.dcn_v1 import DeformConv, deform_conv
+from ..boxes.box_ops import delta2bbox_rotated
+
+
+def bbox_decode(bbox_preds, anchors, means=[0, 0, 0, 0, 0], stds=[1, 1, 1, 1, 1]):
+    """FAM deltas (N,5,H,W) + anchors (H*W,5) -> refined anchors (N,H,W,5)  (s2anet_head.py:631-654).
+    One batched call instead of the reference's per-image Python loop; same arithmetic."""
+    num_imgs, _, H, W = bbox_preds.shape
+    deltas = bbox_preds.permute(0, 2, 3, 1).reshape(-1, 5)
+    rois = anchors.unsqueeze(0).expand(num_imgs, -1, -1).reshape(-1, 5)
+    return delta2bbox_rotated(rois, deltas, means, stds, wh_ratio_clip=1e-6).reshape(num_imgs, H, W, 5)
 
 
 class AlignConv(nn.Module):

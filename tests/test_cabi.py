@@ -78,3 +78,34 @@ def test_install_as_jdet():
     from jdet.ops import box_iou_rotated, box_iou_rotated_v1, roi_align_rotated_v1   # noqa: F401
     from jdet.models.roi_heads.s2anet_head import AlignConv                          # noqa: F401
     assert hasattr(roi_align_rotated_v1, "ROIAlignRotated_v1")
+
+
+def test_box_coders_and_anchors_cpu():
+    """delta2bbox_rotated / bbox_decode / S2ANet grid anchors against a numpy restatement of
+    models/boxes/box_ops.py:229-285, s2anet_head.py:631-654, anchor_generator.py:127-183 (torch ops: CPU is fine)."""
+    import numpy as np
+    from jdet_b200.models.boxes import AnchorGeneratorRotatedS2ANet, delta2bbox_rotated, norm_angle
+    from jdet_b200.models.roi_heads import bbox_decode
+    rng = np.random.default_rng(0)
+    gen = AnchorGeneratorRotatedS2ANet(4, [4.0], [1.0], angles=[0.0])
+    anchors = gen.grid_anchors((6, 7), 8).numpy()
+    assert anchors.shape == (42, 5)
+    assert np.allclose(anchors[0], [1.5, 1.5, 16, 16, 0]) and np.allclose(anchors[8], [9.5, 9.5, 16, 16, 0])   # row-major, x fastest
+    rois = np.concatenate([rng.uniform(0, 100, (50, 2)), rng.uniform(4, 40, (50, 2)), rng.uniform(-1.5, 1.5, (50, 1))], 1).astype(np.float32)
+    deltas = (rng.standard_normal((50, 5)) * 0.5).astype(np.float32)
+    got = delta2bbox_rotated(torch.from_numpy(rois), torch.from_numpy(deltas), wh_ratio_clip=1e-6).numpy()
+    dx, dy, dw, dh, da = deltas.T
+    mr = np.abs(np.log(1e-6))
+    dw, dh = np.clip(dw, -mr, mr), np.clip(dh, -mr, mr)
+    x, y, w, h, a = rois.T
+    gx = dx * w * np.cos(a) - dy * h * np.sin(a) + x
+    gy = dx * w * np.sin(a) + dy * h * np.cos(a) + y
+    ga = (np.pi * da + a + np.pi / 4) % np.pi - np.pi / 4
+    want = np.stack([gx, gy, w * np.exp(dw), h * np.exp(dh), ga], 1)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-4)
+    assert float(norm_angle(torch.tensor(-np.pi / 2))) == pytest.approx(np.pi / 2, abs=1e-6)
+    preds = torch.from_numpy((rng.standard_normal((2, 5, 6, 7)) * 0.3).astype(np.float32))
+    out = bbox_decode(preds, gen.grid_anchors((6, 7), 8))
+    assert out.shape == (2, 6, 7, 5)
+    one = delta2bbox_rotated(gen.grid_anchors((6, 7), 8), preds[1].permute(1, 2, 0).reshape(-1, 5), wh_ratio_clip=1e-6)
+    assert torch.equal(out[1].reshape(-1, 5), one)
