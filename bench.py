@@ -353,7 +353,7 @@ def run_extra(torch, dist, ops, jdist, dev, rank, world, peaks, flush):
             "config": {"workload": "feature_refine points=%d, bs 8 x 256 ch x {128,64,32,16,8}^2 (BASELINE configs[3])" % points},
             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg}}
-    ac = AlignConv(256, 256, 3).to(dev)
+    ac = AlignConv(256, 256, 3).to(dev).requires_grad_(False)     # inference: the fused tcgen05 path
     fn = lambda: [ac(x, a, st) for x, a, (_, st) in zip(xs, an, levels)]
     fn()
     K = 5

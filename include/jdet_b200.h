@@ -99,6 +99,19 @@ int jdet_deform_conv_forward(const float* x, const float* offset, const float* w
                              int dil_h, int dil_w, int groups, int deformable_groups, int relu, float* out,
                              void* stream);
 
+/* DeformConv v1 backward building blocks — replace deformable_im2col / deformable_col2im / deformable_col2im_coord
+ * (ops/dcn_v1.py:309-410, kernels :131-306).  columns / col_grad: (C*kh*kw, B, Ho, Wo).  The two GEMMs of the backward
+ * (W^T x grad_out, grad_out x columns^T — ops/dcn_v1.py:488-489, 545-546) are plain library GEMMs on the caller side. */
+int jdet_deform_im2col(const float* x, const float* offset, int B, int C, int H, int W, int kh, int kw, int stride_h,
+                       int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_groups, float* columns,
+                       void* stream);
+int jdet_deform_col2im(const float* col_grad, const float* offset, int B, int C, int H, int W, int kh, int kw,
+                       int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_groups,
+                       float* grad_x, void* stream);
+int jdet_deform_col2im_coord(const float* col_grad, const float* x, const float* offset, int B, int C, int H, int W, int kh,
+                             int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                             int deformable_groups, float* grad_offset, void* stream);
+
 /* replaces: AlignConv.execute models/roi_heads/s2anet_head.py:715-723 as ONE fused call:
  * offsets from anchors -> deformable 3x3 sampling -> tcgen05 GEMM (3xTF32 split, fp32-class
  * accuracy) -> ReLU.  x (N,C,H,W); anchors (N,H,W,5); weight (Co,C,3,3); out (N,Co,H,W).

@@ -36,6 +36,9 @@ SIGNATURES = {
     "jdet_feature_refine_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p, _p]),
     "jdet_align_conv_offset": (_i, [_p, _i, _i, _i, _f, _i, _p, _p]),
     "jdet_deform_conv_forward": (_i, [_p, _p, _p] + [_i] * 16 + [_p, _p]),
+    "jdet_deform_im2col": (_i, [_p, _p] + [_i] * 13 + [_p, _p]),
+    "jdet_deform_col2im": (_i, [_p, _p] + [_i] * 13 + [_p, _p]),
+    "jdet_deform_col2im_coord": (_i, [_p, _p, _p] + [_i] * 13 + [_p, _p]),
     "jdet_align_conv_forward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "jdet_align_conv_forward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _sz, _p]),
 }

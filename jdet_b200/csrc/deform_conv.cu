@@ -152,6 +152,97 @@ __global__ void __launch_bounds__(256) deform_conv_simt_kernel(const float* __re
   }
 }
 
+// ---- backward building blocks (ops/dcn_v1.py:131-306) ---------------------------------------------
+// columns layout everywhere: [(c*kh*kw + t)][b][ho][wo]  (the reference's), i.e. (K, B*P).
+
+// sampled columns (the forward's A operand, materialised): needed for grad_weight = grad_out x columns^T
+__global__ void __launch_bounds__(256) deform_im2col_kernel(const float* __restrict__ x, const float* __restrict__ offset,
+                                                             DcnShape s, float* __restrict__ col) {
+  const int P = s.Ho * s.Wo, khw = s.kh * s.kw;
+  const long long total = (long long)s.C * s.B * P;
+  const int cpdg = s.C / s.dg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % P);
+    const int b = (int)((idx / P) % s.B);
+    const int c = (int)(idx / ((long long)P * s.B));
+    const int ho = p / s.Wo, wo = p - ho * s.Wo;
+    const float* plane = x + ((size_t)b * s.C + c) * s.H * s.W;
+    const float* off = offset + ((size_t)b * s.dg + c / cpdg) * 2 * khw * P + p;
+    for (int t = 0; t < khw; t++) {
+      const int i = t / s.kw, j = t - i * s.kw;
+      const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + __ldg(off + (size_t)(2 * t) * P);
+      const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + __ldg(off + (size_t)(2 * t + 1) * P);
+      col[(((size_t)c * khw + t) * s.B + b) * P + p] = dcn_sample(plane, s.H, s.W, h_im, w_im);
+    }
+  }
+}
+
+// grad_x: scatter of column gradients with the bilinear weights (deformable_col2im_gpu_kernel :185-241)
+__global__ void __launch_bounds__(256) deform_col2im_kernel(const float* __restrict__ colg, const float* __restrict__ offset,
+                                                             DcnShape s, float* __restrict__ gx) {
+  const int P = s.Ho * s.Wo, khw = s.kh * s.kw;
+  const long long total = (long long)s.C * khw * s.B * P;
+  const int cpdg = s.C / s.dg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % P);
+    const int b = (int)((idx / P) % s.B);
+    const int k = (int)(idx / ((long long)P * s.B));
+    const int c = k / khw, t = k - c * khw;
+    const int i = t / s.kw, j = t - i * s.kw;
+    const int ho = p / s.Wo, wo = p - ho * s.Wo;
+    const float* off = offset + ((size_t)b * s.dg + c / cpdg) * 2 * khw * P + p;
+    const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + __ldg(off + (size_t)(2 * t) * P);
+    const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + __ldg(off + (size_t)(2 * t + 1) * P);
+    if (!(h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W)) continue;
+    const float g = __ldg(colg + idx);
+    const int hl = (int)floorf(h_im), wl = (int)floorf(w_im), hh = hl + 1, wh = wl + 1;
+    const float lh = h_im - (float)hl, lw = w_im - (float)wl, uh = 1.f - lh, uw = 1.f - lw;
+    float* plane = gx + ((size_t)b * s.C + c) * s.H * s.W;
+    if (hl >= 0 && wl >= 0) atomicAdd(plane + hl * s.W + wl, uh * uw * g);
+    if (hl >= 0 && wh <= s.W - 1) atomicAdd(plane + hl * s.W + wh, uh * lw * g);
+    if (hh <= s.H - 1 && wl >= 0) atomicAdd(plane + hh * s.W + wl, lh * uw * g);
+    if (hh <= s.H - 1 && wh <= s.W - 1) atomicAdd(plane + hh * s.W + wh, lh * lw * g);
+  }
+}
+
+// grad_offset: one thread per (b, deformable group, tap, direction pair, position); sums over the
+// group's channels (deformable_col2im_coord_gpu_kernel :243-306, get_coordinate_weight :84-129)
+__global__ void __launch_bounds__(256) deform_col2im_coord_kernel(const float* __restrict__ colg, const float* __restrict__ x,
+                                                                   const float* __restrict__ offset, DcnShape s,
+                                                                   float* __restrict__ goff) {
+  const int P = s.Ho * s.Wo, khw = s.kh * s.kw;
+  const long long total = (long long)s.B * s.dg * khw * P;
+  const int cpdg = s.C / s.dg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % P);
+    const int t = (int)((idx / P) % khw);
+    const int g = (int)((idx / ((long long)P * khw)) % s.dg);
+    const int b = (int)(idx / ((long long)P * khw * s.dg));
+    const int i = t / s.kw, j = t - i * s.kw;
+    const int ho = p / s.Wo, wo = p - ho * s.Wo;
+    const size_t obase = ((size_t)b * s.dg + g) * 2 * khw * P;
+    const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + __ldg(offset + obase + (size_t)(2 * t) * P + p);
+    const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + __ldg(offset + obase + (size_t)(2 * t + 1) * P + p);
+    float gh = 0.f, gw = 0.f;
+    if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {
+      const int hl = (int)floorf(h_im), wl = (int)floorf(w_im), hh = hl + 1, wh = wl + 1;
+      const float lh = h_im - (float)hl, lw = w_im - (float)wl, uh = 1.f - lh, uw = 1.f - lw;
+      const bool v1 = hl >= 0 && wl >= 0, v2 = hl >= 0 && wh <= s.W - 1, v3 = hh <= s.H - 1 && wl >= 0, v4 = hh <= s.H - 1 && wh <= s.W - 1;
+      for (int cc = 0; cc < cpdg; cc++) {
+        const int c = g * cpdg + cc;
+        const float* plane = x + ((size_t)b * s.C + c) * s.H * s.W;
+        const float p1 = v1 ? __ldg(plane + hl * s.W + wl) : 0.f, p2 = v2 ? __ldg(plane + hl * s.W + wh) : 0.f;
+        const float p3 = v3 ? __ldg(plane + hh * s.W + wl) : 0.f, p4 = v4 ? __ldg(plane + hh * s.W + wh) : 0.f;
+        const float cg = __ldg(colg + (((size_t)c * khw + t) * s.B + b) * P + p);
+        gh += (-uw * p1 - lw * p2 + uw * p3 + lw * p4) * cg;
+        gw += (-uh * p1 + uh * p2 - lh * p3 + lh * p4) * cg;
+      }
+    }
+    goff[obase + (size_t)(2 * t) * P + p] = gh;
+    goff[obase + (size_t)(2 * t + 1) * P + p] = gw;
+  }
+}
+
 }  // namespace jdet
 
 // AlignConv.get_offset for a batch (s2anet_head.py:677-721): anchors (N,H,W,5) image space ->
@@ -187,5 +278,57 @@ JDET_API int jdet_deform_conv_forward(const float* x, const float* offset, const
   const long long M = (long long)B * s.Ho * s.Wo;
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)jdet_ceil_div(Co / groups, BN), (unsigned)groups);
   deform_conv_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, offset, weight, s, relu, out);
+  return (int)cudaGetLastError();
+}
+
+// ---- backward building blocks, C ABI (the two GEMMs between them are plain library GEMMs on the host side)
+static int jdet_dcn_shape(jdet::DcnShape* s, int B, int C, int H, int W, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                          int pad_w, int dil_h, int dil_w, int dg) {
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0 || stride_h <= 0 || stride_w <= 0 || dil_h <= 0 ||
+      dil_w <= 0 || dg <= 0 || C % dg)
+    return JDET_ERR_BAD_ARG;
+  *s = jdet::DcnShape{B, C, H, W, 0, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, 1, dg, 0, 0};
+  s->Ho = (H + 2 * pad_h - (dil_h * (kh - 1) + 1)) / stride_h + 1;
+  s->Wo = (W + 2 * pad_w - (dil_w * (kw - 1) + 1)) / stride_w + 1;
+  return (s->Ho <= 0 || s->Wo <= 0) ? JDET_ERR_BAD_ARG : 0;
+}
+
+// replaces deformable_im2col (ops/dcn_v1.py:309-339): columns (C*kh*kw, B, Ho, Wo)
+JDET_API int jdet_deform_im2col(const float* x, const float* offset, int B, int C, int H, int W, int kh, int kw, int stride_h,
+                                int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int deformable_groups,
+                                float* columns, void* stream) {
+  jdet::DcnShape s;
+  const int e = jdet_dcn_shape(&s, B, C, H, W, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, deformable_groups);
+  if (e) return e;
+  if (B == 0) return 0;
+  if (!x || !offset || !columns) return JDET_ERR_BAD_ARG;
+  jdet::deform_im2col_kernel<<<jdet::kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(x, offset, s, columns);
+  return (int)cudaGetLastError();
+}
+
+// replaces deformable_col2im (ops/dcn_v1.py:376-410): columns gradient (C*kh*kw, B, Ho, Wo) -> grad_x (B,C,H,W), fully written
+JDET_API int jdet_deform_col2im(const float* col_grad, const float* offset, int B, int C, int H, int W, int kh, int kw,
+                                int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                                int deformable_groups, float* grad_x, void* stream) {
+  jdet::DcnShape s;
+  const int e = jdet_dcn_shape(&s, B, C, H, W, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, deformable_groups);
+  if (e) return e;
+  if (B == 0) return 0;
+  if (!col_grad || !offset || !grad_x) return JDET_ERR_BAD_ARG;
+  JDET_RETURN_IF_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)B * C * H * W * 4, (cudaStream_t)stream));
+  jdet::deform_col2im_kernel<<<jdet::kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(col_grad, offset, s, grad_x);
+  return (int)cudaGetLastError();
+}
+
+// replaces deformable_col2im_coord (ops/dcn_v1.py:341-374): -> grad_offset (B, dg*2*kh*kw, Ho, Wo), fully written
+JDET_API int jdet_deform_col2im_coord(const float* col_grad, const float* x, const float* offset, int B, int C, int H, int W,
+                                      int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                                      int deformable_groups, float* grad_offset, void* stream) {
+  jdet::DcnShape s;
+  const int e = jdet_dcn_shape(&s, B, C, H, W, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, deformable_groups);
+  if (e) return e;
+  if (B == 0) return 0;
+  if (!col_grad || !x || !offset || !grad_offset) return JDET_ERR_BAD_ARG;
+  jdet::deform_col2im_coord_kernel<<<jdet::kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(col_grad, x, offset, s, grad_offset);
   return (int)cudaGetLastError();
 }

@@ -7,7 +7,7 @@ import torch
 from torch import nn
 
 from ...ops._common import check, f32c, lib, require_cuda, scratch, stream_ptr
-from ...ops.dcn_v1 import DeformConv, deform_conv
+from ...ops.dcn_v1 import DeformConv, _deform_conv_bwd, deform_conv
 from ..boxes.box_ops import delta2bbox_rotated
 
 
@@ -18,6 +18,27 @@ def bbox_decode(bbox_preds, anchors, means=[0, 0, 0, 0, 0], stds=[1, 1, 1, 1, 1]
     deltas = bbox_preds.permute(0, 2, 3, 1).reshape(-1, 5)
     rois = anchors.unsqueeze(0).expand(num_imgs, -1, -1).reshape(-1, 5)
     return delta2bbox_rotated(rois, deltas, means, stds, wh_ratio_clip=1e-6).reshape(num_imgs, H, W, 5)
+
+
+class _AlignConvFn(torch.autograd.Function):
+    """Training path of the fused AlignConv: forward is the same tcgen05 kernel; backward goes through ReLU'
+    (out > 0) and the DeformConv backward with the offsets recomputed from the anchors (they carry no gradient)."""
+
+    @staticmethod
+    def forward(ctx, module, x, anchors, weight, stride):
+        out = module._fused(x, anchors, weight.detach(), stride)
+        ctx.module, ctx.stride = module, stride
+        ctx.save_for_backward(x, anchors, weight, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, anchors, weight, out = ctx.saved_tensors
+        offset = ctx.module.get_offset_batched(anchors, ctx.stride)
+        g = grad_output * (out > 0).to(grad_output.dtype)
+        gx, _, gw = _deform_conv_bwd(x, offset, weight, g, (1, 1), (1, 1), (1, 1), 1,
+                                     ctx.needs_input_grad[1], False, ctx.needs_input_grad[3])
+        return None, gx, None, gw, None
 
 
 class AlignConv(nn.Module):
@@ -50,26 +71,33 @@ class AlignConv(nn.Module):
                                                    stream_ptr(a.device)), "align_conv_offset")
         return off
 
+    def _fused(self, x, anchors, weight, stride):
+        xx, aa, w = f32c(x), f32c(anchors), f32c(weight)
+        N, H, W = aa.shape[:3]
+        C, Co = xx.shape[1], w.shape[0]
+        out = torch.empty((N, Co, H, W), dtype=torch.float32, device=xx.device)
+        if out.numel() == 0:
+            return out
+        L = lib()
+        with torch.cuda.device(xx.device):
+            ws = scratch(L.jdet_align_conv_forward_workspace_bytes(N, C, H, W, Co), xx.device)
+            check(L.jdet_align_conv_forward(xx.data_ptr(), aa.data_ptr(), w.data_ptr(), N, C, H, W, Co,
+                                            float(stride), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            stream_ptr(xx.device)), "align_conv")
+        return out
+
     def forward(self, x, anchors, stride):
         """x (N,C,H,W), anchors (N,H,W,5) image space -> relu(deform_conv(x, offset(anchors)))."""
         require_cuda(x, anchors)
         dc = self.deform_conv
-        N, H, W = anchors.shape[:3]
-        if self.kernel_size == 3 and dc.deformable_groups == 1 and dc.groups == 1:
-            xx, aa, w = f32c(x), f32c(anchors), f32c(dc.weight.detach())
-            C, Co = xx.shape[1], w.shape[0]
-            out = torch.empty((N, Co, H, W), dtype=torch.float32, device=xx.device)
-            if out.numel() == 0:
-                return out
-            L = lib()
-            with torch.cuda.device(xx.device):
-                ws = scratch(L.jdet_align_conv_forward_workspace_bytes(N, C, H, W, Co), xx.device)
-                check(L.jdet_align_conv_forward(xx.data_ptr(), aa.data_ptr(), w.data_ptr(), N, C, H, W, Co,
-                                                float(stride), out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                stream_ptr(xx.device)), "align_conv")
-            return out
-        offset = self.get_offset_batched(anchors, stride)
-        return deform_conv(x, offset, dc.weight.detach(), dc.stride, dc.padding, dc.dilation, dc.groups,
+        fused = self.kernel_size == 3 and dc.deformable_groups == 1 and dc.groups == 1
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or dc.weight.requires_grad)
+        if fused and not needs_grad:
+            return self._fused(x, anchors, dc.weight.detach(), stride)
+        if fused:
+            return _AlignConvFn.apply(self, x, anchors, dc.weight, stride)
+        offset = self.get_offset_batched(anchors, stride)      # no gradient, as in the reference (@jt.no_grad, :676)
+        return deform_conv(x, offset, dc.weight, dc.stride, dc.padding, dc.dilation, dc.groups,
                            dc.deformable_groups, _relu=True)
 
     execute = forward

@@ -244,6 +244,17 @@ def deform_conv(x, offset, weight, stride=1, padding=0, dilation=1, deformable_g
     return out
 
 
+def deform_conv_backward(x, offset, weight, grad_out, stride=1, padding=0, dilation=1, deformable_groups=1):
+    """-> (grad_x, grad_offset, grad_weight), groups = 1 (ops/dcn_v1.py:457-556)."""
+    x, offset, weight, grad_out = _f32(x), _f32(offset), _f32(weight), _f32(grad_out)
+    B, C, H, W = x.shape
+    Co, _, kh, kw = weight.shape
+    gx, go, gw = np.zeros_like(x), np.zeros_like(offset), np.zeros_like(weight)
+    lib().orc_deform_conv_backward(_p(x), _p(offset), _p(weight), _p(grad_out), B, C, H, W, Co, kh, kw, stride, stride,
+                                   padding, padding, dilation, dilation, deformable_groups, _p(gx), _p(go), _p(gw))
+    return gx, go, gw
+
+
 def deform_im2col(x, offset, kh, kw, stride=1, padding=0, dilation=1, deformable_groups=1):
     x, offset = _f32(x), _f32(offset)
     B, C, H, W = x.shape

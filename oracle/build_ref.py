@@ -318,6 +318,34 @@ static void launch_im2col(const float* in0_p, const float* in1_p, int channels, 
       dilation_h, dilation_w, channel_per_deformable_group, parallel_imgs, channels,
       deformable_group, height_col, width_col, out0_p);
 }}
+// launches of deformable_col2im / deformable_col2im_coord: ops/dcn_v1.py:341-410 (memset + kernel)
+static void launch_col2im(const float* in0_p, const float* in1_p, int channels, int height, int width, int ksize_h,
+                          int ksize_w, int pad_h, int pad_w, int stride_h, int stride_w, int dilation_h, int dilation_w,
+                          int parallel_imgs, int deformable_group, float* out0_p, cudaStream_t st) {{
+  int height_col = (height + 2 * pad_h - (dilation_h * (ksize_h - 1) + 1)) / stride_h + 1;
+  int width_col = (width + 2 * pad_w - (dilation_w * (ksize_w - 1) + 1)) / stride_w + 1;
+  int num_kernels = channels * ksize_h * ksize_w * height_col * width_col * parallel_imgs;
+  int channel_per_deformable_group = channels / deformable_group;
+  cudaMemsetAsync(out0_p, 0, (size_t)parallel_imgs * channels * height * width * 4, st);
+  deformable_col2im_gpu_kernel<float><<<GET_BLOCKS(num_kernels), CUDA_NUM_THREADS, 0, st>>>(
+      num_kernels, in0_p, in1_p, channels, height, width, ksize_h, ksize_w, pad_h, pad_w, stride_h, stride_w,
+      dilation_h, dilation_w, channel_per_deformable_group, parallel_imgs, deformable_group, height_col, width_col,
+      out0_p, 0);
+}}
+static void launch_col2im_coord(const float* in0_p, const float* in1_p, const float* in2_p, int channels, int height,
+                                int width, int ksize_h, int ksize_w, int pad_h, int pad_w, int stride_h, int stride_w,
+                                int dilation_h, int dilation_w, int parallel_imgs, int deformable_group, float* out0_p,
+                                cudaStream_t st) {{
+  int height_col = (height + 2 * pad_h - (dilation_h * (ksize_h - 1) + 1)) / stride_h + 1;
+  int width_col = (width + 2 * pad_w - (dilation_w * (ksize_w - 1) + 1)) / stride_w + 1;
+  int num_kernels = height_col * width_col * 2 * ksize_h * ksize_w * deformable_group * parallel_imgs;
+  int channel_per_deformable_group = channels * ksize_h * ksize_w / deformable_group;
+  cudaMemsetAsync(out0_p, 0, (size_t)num_kernels * 4, st);
+  deformable_col2im_coord_gpu_kernel<float><<<GET_BLOCKS(num_kernels), CUDA_NUM_THREADS, 0, st>>>(
+      num_kernels, in0_p, in1_p, in2_p, channels, height, width, ksize_h, ksize_w, pad_h, pad_w, stride_h, stride_w,
+      dilation_h, dilation_w, channel_per_deformable_group, parallel_imgs, 2 * ksize_h * ksize_w * deformable_group,
+      deformable_group, height_col, width_col, out0_p);
+}}
 }}  // namespace ref_dcn
 """)
 
@@ -367,6 +395,21 @@ int ref_feature_refine_backward_cuda(const float* grad, const float* boxes, int 
 int ref_feature_refine_cuda(const float* feat, const float* boxes, int n, int c, int h, int w,
                             int points, float spatial_scale, float* out, void* st) {
   ref_fr::launch(feat, boxes, n, c, h, w, points, spatial_scale, out, (cudaStream_t)st);
+  return (int)cudaGetLastError();
+}
+int ref_deformable_col2im_cuda(const float* col, const float* offset, int channels, int height, int width, int kh, int kw,
+                               int pad_h, int pad_w, int stride_h, int stride_w, int dil_h, int dil_w, int parallel_imgs,
+                               int deformable_group, float* grad_im, void* st) {
+  ref_dcn::launch_col2im(col, offset, channels, height, width, kh, kw, pad_h, pad_w, stride_h, stride_w, dil_h, dil_w,
+                         parallel_imgs, deformable_group, grad_im, (cudaStream_t)st);
+  return (int)cudaGetLastError();
+}
+int ref_deformable_col2im_coord_cuda(const float* col, const float* im, const float* offset, int channels, int height,
+                                     int width, int kh, int kw, int pad_h, int pad_w, int stride_h, int stride_w,
+                                     int dil_h, int dil_w, int parallel_imgs, int deformable_group, float* grad_offset,
+                                     void* st) {
+  ref_dcn::launch_col2im_coord(col, im, offset, channels, height, width, kh, kw, pad_h, pad_w, stride_h, stride_w,
+                               dil_h, dil_w, parallel_imgs, deformable_group, grad_offset, (cudaStream_t)st);
   return (int)cudaGetLastError();
 }
 int ref_deformable_im2col_cuda(const float* im, const float* offset, int channels, int height,

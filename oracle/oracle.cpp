@@ -530,6 +530,71 @@ void orc_deform_conv(const float* x, const float* offset, const float* weight, i
   }
 }
 
+// DeformConv v1 backward (ops/dcn_v1.py:185-306 kernels, 457-556 host flow), groups = 1:
+//   grad_x      : deformable_col2im        — bilinear weights of get_gradient_weight (:58-82) on in-image corners
+//   grad_offset : deformable_col2im_coord  — get_coordinate_weight (:84-129), 0 outside (-1,H)x(-1,W)
+//   grad_weight : grad_out x columns^T     — columns from deformable_im2col
+// Everything accumulates in double (the reference: float atomics + SGEMM).
+void orc_deform_conv_backward(const float* x, const float* offset, const float* weight, const float* grad_out, int B, int C,
+                              int H, int W, int Co, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w,
+                              int dil_h, int dil_w, int dg, float* gx, float* goff, float* gw) {
+  const int Ho = (H + 2 * pad_h - (dil_h * (kh - 1) + 1)) / stride_h + 1;
+  const int Wo = (W + 2 * pad_w - (dil_w * (kw - 1) + 1)) / stride_w + 1;
+  const int cpg = C / dg, khw = kh * kw, K = C * khw, P = Ho * Wo;
+  std::vector<double> ax((size_t)B * C * H * W, 0.0), ao((size_t)B * dg * 2 * khw * P, 0.0), aw((size_t)Co * K, 0.0);
+  std::vector<double> colg(K);
+  for (int b = 0; b < B; b++)
+    for (int p = 0; p < P; p++) {
+      const int ho = p / Wo, wo = p % Wo;
+      // column gradient of this output position: W^T x grad_out
+      for (int k = 0; k < K; k++) colg[k] = 0.0;
+      for (int co = 0; co < Co; co++) {
+        const double g = grad_out[(((size_t)b * Co + co) * Ho + ho) * Wo + wo];
+        if (g == 0.0) continue;
+        const float* wr = weight + (size_t)co * K;
+        for (int k = 0; k < K; k++) colg[k] += (double)wr[k] * g;
+      }
+      for (int c = 0; c < C; c++) {
+        const float* plane = x + ((size_t)b * C + c) * H * W;
+        const int g = c / cpg;
+        const float* off = offset + ((size_t)b * dg + g) * 2 * khw * P;
+        for (int t = 0; t < khw; t++) {
+          const int i = t / kw, j = t % kw;
+          const float oh = off[(size_t)(2 * t) * P + p], ow = off[(size_t)(2 * t + 1) * P + p];
+          const float h_im = (ho * stride_h - pad_h) + i * dil_h + oh;
+          const float w_im = (wo * stride_w - pad_w) + j * dil_w + ow;
+          const double cg = colg[(size_t)c * khw + t];
+          // forward sample for grad_weight
+          float v = 0.f;
+          const bool inside = h_im > -1 && w_im > -1 && h_im < H && w_im < W;
+          if (inside) v = bilinear_zeropad(plane, H, W, h_im, w_im);
+          for (int co = 0; co < Co; co++)
+            aw[(size_t)co * K + (size_t)c * khw + t] += (double)grad_out[(((size_t)b * Co + co) * Ho + ho) * Wo + wo] * v;
+          if (!inside) continue;
+          const int hl = (int)std::floor(h_im), wl = (int)std::floor(w_im), hh = hl + 1, wh = wl + 1;
+          const double lh = (double)h_im - hl, lw = (double)w_im - wl;
+          const double uh = 1.0 - lh, uw = 1.0 - lw;
+          double* gplane = ax.data() + ((size_t)b * C + c) * H * W;
+          const bool v1 = hl >= 0 && wl >= 0, v2 = hl >= 0 && wh <= W - 1, v3 = hh <= H - 1 && wl >= 0, v4 = hh <= H - 1 && wh <= W - 1;
+          if (v1) gplane[hl * W + wl] += uh * uw * cg;
+          if (v2) gplane[hl * W + wh] += uh * lw * cg;
+          if (v3) gplane[hh * W + wl] += lh * uw * cg;
+          if (v4) gplane[hh * W + wh] += lh * lw * cg;
+          const double p1 = v1 ? plane[hl * W + wl] : 0.0, p2 = v2 ? plane[hl * W + wh] : 0.0;
+          const double p3 = v3 ? plane[hh * W + wl] : 0.0, p4 = v4 ? plane[hh * W + wh] : 0.0;
+          const double dh_w = -uw * p1 - lw * p2 + uw * p3 + lw * p4;    // d sample / d h   (bp_dir 0)
+          const double dw_w = -uh * p1 + uh * p2 - lh * p3 + lh * p4;    // d sample / d w   (bp_dir 1)
+          double* go = ao.data() + ((size_t)b * dg + g) * 2 * khw * P;
+          go[(size_t)(2 * t) * P + p] += dh_w * cg;
+          go[(size_t)(2 * t + 1) * P + p] += dw_w * cg;
+        }
+      }
+    }
+  for (size_t i = 0; i < ax.size(); i++) gx[i] = (float)ax[i];
+  for (size_t i = 0; i < ao.size(); i++) goff[i] = (float)ao[i];
+  for (size_t i = 0; i < aw.size(); i++) gw[i] = (float)aw[i];
+}
+
 // ops/dcn_v1.py:131-184 alone: columns (C*kh*kw, B, Ho, Wo) as the reference lays them out.
 void orc_deform_im2col(const float* x, const float* offset, int B, int C, int H, int W, int kh, int kw,
                        int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int dg,

@@ -101,3 +101,21 @@ def deform_conv(x, offset, weight, stride=1, pad=0, dil=1, dg=1):
     torch.backends.cuda.matmul.allow_tf32 = prev
     torch.cuda.synchronize()
     return out.reshape(Co, B, Ho, Wo).permute(1, 0, 2, 3).contiguous()
+
+
+def deform_col2im(colg, offset, B, C, H, W, k, stride, pad, dil, dg):
+    R = oracle.ref_cuda()
+    out = torch.empty((B, C, H, W), device="cuda")
+    assert R.ref_deformable_col2im_cuda(_p(colg), _p(offset), C, H, W, k, k, pad, pad, stride, stride, dil, dil, B, dg, _p(out), _st()) == 0
+    torch.cuda.synchronize()
+    return out
+
+
+def deform_col2im_coord(colg, x, offset, k, stride, pad, dil, dg):
+    R = oracle.ref_cuda()
+    B, C, H, W = x.shape
+    out = torch.empty_like(offset)
+    assert R.ref_deformable_col2im_coord_cuda(_p(colg), _p(x), _p(offset), C, H, W, k, k, pad, pad, stride, stride, dil, dil, B, dg,
+                                              _p(out), _st()) == 0
+    torch.cuda.synchronize()
+    return out

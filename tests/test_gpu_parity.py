@@ -398,13 +398,70 @@ def test_align_conv_vs_oracle(shape):
     x = rng.standard_normal((N, C, H, W)).astype(np.float32)
     a = s2anet_anchors(rng, N, H, W, stride)
     w = m.deform_conv.weight.detach().cpu().numpy()
-    got = m(cu(x), cu(a), stride).cpu().numpy()
+    with torch.no_grad():
+        got = m(cu(x), cu(a), stride).cpu().numpy()
     want = oracle.align_conv(x, a, stride, w)
     assert got.shape == (N, Co, H, W) and (got >= 0).all()
     assert np.abs(got - want).max() <= TOL, np.abs(got - want).max()
     off = m.get_offset_batched(cu(a), stride).cpu().numpy()
     assert np.abs(off - oracle.align_conv_offset(a, stride)).max() <= 1e-4
     assert np.array_equal(m.get_offset(cu(a[0].reshape(-1, 5)), (H, W), stride).cpu().numpy(), off[0])
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, C=16, H=12, W=14, Co=24, k=3, stride=1, pad=1, dil=1, dg=1),
+    dict(B=3, C=8, H=15, W=13, Co=12, k=3, stride=2, pad=1, dil=2, dg=2),
+])
+def test_deform_conv_backward(cfg):
+    rng = np.random.default_rng(cfg["Co"] + 1)
+    B, C, H, W, Co, k = cfg["B"], cfg["C"], cfg["H"], cfg["W"], cfg["Co"], cfg["k"]
+    Ho = (H + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    Wo = (W + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    off = (rng.standard_normal((B, cfg["dg"] * 2 * k * k, Ho, Wo)) * 1.5).astype(np.float32)
+    w = (rng.standard_normal((Co, C, k, k)) * 0.2).astype(np.float32)
+    go = rng.standard_normal((B, Co, Ho, Wo)).astype(np.float32)
+    xt, ot, wt = cu(x).requires_grad_(True), cu(off).requires_grad_(True), cu(w).requires_grad_(True)
+    out = ops().dcn_v1.deform_conv(xt, ot, wt, cfg["stride"], cfg["pad"], cfg["dil"], 1, cfg["dg"])
+    out.backward(cu(go))
+    wx, wo_, ww = oracle.deform_conv_backward(x, off, w, go, cfg["stride"], cfg["pad"], cfg["dil"], cfg["dg"])
+    assert np.abs(xt.grad.cpu().numpy() - wx).max() <= BWD_TOL
+    assert np.abs(ot.grad.cpu().numpy() - wo_).max() <= 5e-4        # sums C products of O(1) terms in fp32
+    assert np.abs(wt.grad.cpu().numpy() - ww).max() <= 5e-4
+    if _refcuda.available():   # the reference's own col2im / col2im_coord kernels on the same column gradient
+        colg = (cu(w).reshape(Co, -1).t() @ cu(go).permute(1, 0, 2, 3).reshape(Co, -1)).contiguous()
+        r_x = _refcuda.deform_col2im(colg, cu(off), B, C, H, W, k, cfg["stride"], cfg["pad"], cfg["dil"], cfg["dg"]).cpu().numpy()
+        r_o = _refcuda.deform_col2im_coord(colg, cu(x), cu(off), k, cfg["stride"], cfg["pad"], cfg["dil"], cfg["dg"]).cpu().numpy()
+        assert np.abs(xt.grad.cpu().numpy() - r_x).max() <= 5e-4
+        assert np.abs(ot.grad.cpu().numpy() - r_o).max() <= 5e-4
+
+
+def test_align_conv_backward():
+    rng = np.random.default_rng(77)
+    N, C, H, W, Co, stride = 2, 32, 10, 12, 64, 8
+    from jdet_b200.models.roi_heads.s2anet_head import AlignConv
+    m = AlignConv(C, Co, 3).cuda()
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    a = s2anet_anchors(rng, N, H, W, stride)
+    go = rng.standard_normal((N, Co, H, W)).astype(np.float32)
+    w = m.deform_conv.weight.detach().cpu().numpy()
+    xt = cu(x).requires_grad_(True)
+    out = m(xt, cu(a), stride)
+    out.backward(cu(go))
+    off = oracle.align_conv_offset(a, stride)
+    fwd = oracle.deform_conv(x, off, w, 1, 1, 1, 1, relu=True)
+    assert np.abs(out.detach().cpu().numpy() - fwd).max() <= TOL
+    g = go * (fwd > 0)
+    near = np.abs(oracle.deform_conv(x, off, w, 1, 1, 1, 1)) < 1e-4      # ReLU kink: sign may differ within tolerance
+    g[near] = 0
+    go2 = go.copy()
+    go2[near] = 0
+    xt2 = cu(x).requires_grad_(True)
+    m.zero_grad()
+    m(xt2, cu(a), stride).backward(cu(go2))
+    wx, _, ww = oracle.deform_conv_backward(x, off, w, g, 1, 1, 1, 1)
+    assert np.abs(xt2.grad.cpu().numpy() - wx).max() <= 5e-4
+    assert np.abs(m.deform_conv.weight.grad.cpu().numpy() - ww).max() <= 2e-3   # sums N*H*W = 240 products per weight
 
 
 # ------------------------------------------------------------------------------------ callers

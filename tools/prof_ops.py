@@ -50,7 +50,7 @@ if want("fr") or want("ac"):
             ops.fr.feature_refine(x, bx, 1 / 8., 1)
             ops.fr.feature_refine(x, bx, 1 / 8., 5)
     if want("ac"):
-        m = AlignConv(256, 256, 3).to(dev)
+        m = AlignConv(256, 256, 3).to(dev).requires_grad_(False)
         for _ in range(a.reps):
             m(x, an, 8)
 torch.cuda.synchronize()

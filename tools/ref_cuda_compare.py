@@ -77,7 +77,7 @@ for pts in (1, 5):
     ours = timeit(lambda: ops.fr.feature_refine(x, bx, 1 / 8., pts))
     ref = timeit(lambda: _refcuda.feature_refine(x, bx, 1 / 8., pts))
     res["feature_refine points=%d, 8x256x128x128" % pts] = {"ours_ms": ours, "reference_cuda_kernel_ms": ref, "speedup": ref / ours}
-m = AlignConv(256, 256, 3).to(dev)
+m = AlignConv(256, 256, 3).to(dev).requires_grad_(False)
 w = m.deform_conv.weight.detach()
 ours = timeit(lambda: m(x, an, 8), 5)
 off = m.get_offset_batched(an, 8)
