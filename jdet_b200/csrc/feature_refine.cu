@@ -163,6 +163,139 @@ __global__ void __launch_bounds__(256, 2) feature_refine_bwd_kernel(const float*
   }
 }
 
+// ---- TMA-staged kernel --------------------------------------------------------------------------
+// Full-width row bands of an NCHW plane are contiguous, so the band a CTA works on (its rows plus kHalo
+// rows above and below) is ONE cp.async.bulk (UBLKCP) per channel into a shared-memory ring guarded by
+// mbarriers: kStages channels are in flight per CTA with no registers tied up, which is what an HBM
+// stream with a short gather needs.  Centre reads and taps are then served from shared memory (lanes are
+// consecutive pixels: conflict-light); a sample whose taps leave the band falls back to global loads.
+// CTA = (row band, channel slab, image), one thread per pixel of the band.
+namespace fr_tma {
+
+constexpr int kHalo = 4;
+constexpr int kMaxStages = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int POINTS>
+__global__ void __launch_bounds__(1024) feature_refine_tma_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
+                                                                   int C, int H, int W, float spatial_scale, int rows_per_band,
+                                                                   int ch_per_cta, int stages, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int HW = H * W;
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
+  const int r0 = blockIdx.x * rows_per_band;                       // first output row of this band
+  const int lo = max(0, r0 - kHalo), hi = min(H, r0 + rows_per_band + kHalo);   // staged rows [lo, hi)
+  const int band_elems = (hi - lo) * W;
+  const uint32_t band_bytes = (uint32_t)band_elems * 4u;
+  const int stage_elems = (rows_per_band + 2 * kHalo) * W;
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * stage_elems);
+  uint64_t* empty = full + kMaxStages;
+  const int tid = threadIdx.x, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int nch = c1 - c0;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const float* src0 = feat + ((size_t)n * C + c0) * HW + (size_t)lo * W;
+  if (tid == 0) {
+    for (int s = 0; s < stages && s < nch; s++) {
+      mbar_expect_tx(&full[s], band_bytes);
+      bulk_g2s(ring + (size_t)s * stage_elems, src0 + (size_t)s * HW, band_bytes, &full[s]);
+    }
+  }
+
+  // this thread's pixel and its taps (band-relative offsets when every corner is staged)
+  const int row = r0 + tid / W, col = tid - (tid / W) * W;
+  const bool active = tid < rows_per_band * W && row < H;
+  const int p = row * W + col;
+  Tap4 taps[POINTS];
+  bool staged[POINTS];
+  if (active) {
+    const float* bb = boxes + ((size_t)n * HW + p) * 5;
+    const float roi_y = __fmul_rn(__ldg(bb), spatial_scale), roi_x = __fmul_rn(__ldg(bb + 1), spatial_scale);
+    taps[0] = fr_tap(roi_y, roi_x, H, W);
+    if (POINTS > 1) {
+      const float rw = __fmul_rn(__ldg(bb + 2), spatial_scale), rh = __fmul_rn(__ldg(bb + 3), spatial_scale), ra = __ldg(bb + 4);
+      const float w2 = rw * 0.5f, h2 = rh * 0.5f;
+      const float ca = cosf(ra), sa = sinf(ra);
+      const float wx = __fmul_rn(ca, w2), wy = __fmul_rn(sa, w2), hx = __fmul_rn(-sa, h2), hy = __fmul_rn(ca, h2);
+      taps[1 % POINTS] = fr_tap(__fadd_rn(__fadd_rn(roi_y, wy), hy), __fadd_rn(__fadd_rn(roi_x, wx), hx), H, W);
+      taps[2 % POINTS] = fr_tap(__fadd_rn(__fsub_rn(roi_y, wy), hy), __fadd_rn(__fsub_rn(roi_x, wx), hx), H, W);
+      taps[3 % POINTS] = fr_tap(__fsub_rn(__fsub_rn(roi_y, wy), hy), __fsub_rn(__fsub_rn(roi_x, wx), hx), H, W);
+      taps[4 % POINTS] = fr_tap(__fsub_rn(__fadd_rn(roi_y, wy), hy), __fsub_rn(__fadd_rn(roi_x, wx), hx), H, W);
+    }
+    const int blo = lo * W, bhi = hi * W;
+#pragma unroll
+    for (int i = 0; i < POINTS; i++) {
+      Tap4& t = taps[i];
+      staged[i] = t.o00 >= 0 && t.o00 >= blo && t.o11 < bhi;       // o00 is the smallest, o11 the largest offset
+      if (staged[i]) { t.o00 -= blo; t.o01 -= blo; t.o10 -= blo; t.o11 -= blo; }
+    }
+  }
+  const int pc = p - lo * W;                                       // centre, band-relative
+  float* dst = out + ((size_t)n * C + c0) * HW + p;
+  const float* gplane = feat + ((size_t)n * C + c0) * HW;
+
+  uint32_t stage = 0, phase = 0;
+  for (int c = 0; c < nch; c++) {
+    mbar_wait(&full[stage], phase);
+    const float* sp = ring + (size_t)stage * stage_elems;
+    if (active) {
+      float v = sp[pc];
+#pragma unroll
+      for (int i = 0; i < POINTS; i++) {
+        const Tap4& t = taps[i];
+        if (staged[i]) v += t.w1 * sp[t.o00] + t.w2 * sp[t.o01] + t.w3 * sp[t.o10] + t.w4 * sp[t.o11];
+        else if (t.o00 >= 0)
+          v += t.w1 * __ldg(gplane + t.o00) + t.w2 * __ldg(gplane + t.o01) + t.w3 * __ldg(gplane + t.o10) + t.w4 * __ldg(gplane + t.o11);
+      }
+      st_stream(dst, v);
+    }
+    dst += HW;
+    gplane += HW;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (tid == 0 && c + stages < nch) {                            // refill this slot with channel c + stages
+      mbar_wait(&empty[stage], phase);
+      mbar_expect_tx(&full[stage], band_bytes);
+      bulk_g2s(ring + (size_t)stage * stage_elems, src0 + (size_t)(c + stages) * HW, band_bytes, &full[stage]);
+    }
+    if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+  }
+}
+
+}  // namespace fr_tma
+
 }  // namespace jdet
 
 // jdet.ops.fr.feature_refine(features, best_rbboxes, spatial_scale, points) (ops/fr.py:255-273)
@@ -175,6 +308,31 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
   if (N > 65535) return JDET_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W;
+  // TMA-staged path: full-width row bands (contiguous in NCHW), one thread per pixel of the band
+  if (W % 4 == 0 && W <= 1024 && ((uintptr_t)features & 15) == 0) {
+    using namespace fr_tma;
+    const int max_threads = points == 1 ? 1024 : 512;
+    const int rows = max(1, min(H, max_threads / W));
+    const int threads = jdet_align_up((size_t)rows * W, 32);
+    const int stage_elems = (rows + 2 * kHalo) * W;
+    int stages = (int)((150 * 1024) / ((size_t)stage_elems * 4));
+    stages = stages > kMaxStages ? kMaxStages : stages;
+    if (stages >= 2) {
+      const int bands = jdet_ceil_div(H, rows);
+      int cpc = C;
+      while (cpc > 4 * stages && (long long)bands * jdet_ceil_div(C, cpc) * N < 148 * 2) cpc = (cpc + 1) / 2;
+      const size_t smem = (size_t)stages * stage_elems * 4 + 2 * kMaxStages * sizeof(uint64_t);
+      dim3 g(bands, jdet_ceil_div(C, cpc), N);
+      if (points == 1) {
+        JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        feature_refine_tma_kernel<1><<<g, threads, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output);
+      } else {
+        JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        feature_refine_tma_kernel<5><<<g, threads, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output);
+      }
+      return (int)cudaGetLastError();
+    }
+  }
   const int ptiles = jdet_ceil_div(HW, 256);
   // enough CTAs to fill 148 SMs several times over, but keep slabs long enough to amortise the box decode
   int ch_per_cta = C;

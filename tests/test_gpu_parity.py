@@ -280,6 +280,8 @@ def test_feature_refine_vs_oracle(points, W):
     a = s2anet_anchors(rng, N, H, W, stride)
     boxes = a[..., [1, 0, 2, 3, 4]].copy()       # the op reads bbox[0] as the row coordinate
     boxes[0, 0, :8, :2] = [[-50, -50]] * 4 + [[1e4, 3]] * 4     # out-of-map samples
+    boxes[1, 3, :6, :2] = [[(H - 1) * stride, 2 * stride], [0, (W - 1) * stride]] * 3   # in-map but far from the pixel's row band
+    boxes[1, 20, 5:9, 2:4] *= 6                                  # huge boxes: corner samples leave the band
     got = ops().fr.feature_refine(cu(x), cu(boxes), 1 / stride, points).cpu().numpy()
     want = oracle.feature_refine(x, boxes, 1 / stride, points)
     assert np.abs(got - want).max() <= TOL, np.abs(got - want).max()
