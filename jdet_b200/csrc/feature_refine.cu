@@ -325,9 +325,12 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
       dim3 g(bands, jdet_ceil_div(C, cpc), N);
       if (points == 1) {
         JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // without this the driver picks the smallest carve-out that fits ONE block (ncu: occupancy_limit_shared_mem = 1)
+        JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         feature_refine_tma_kernel<1><<<g, threads, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output);
       } else {
         JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         feature_refine_tma_kernel<5><<<g, threads, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output);
       }
       return (int)cudaGetLastError();

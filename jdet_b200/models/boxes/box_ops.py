@@ -33,3 +33,18 @@ def delta2bbox_rotated(rois, deltas, means=(0., 0., 0., 0., 0.), stds=(1., 1., 1
     gh = roi_h * dh.exp()
     ga = norm_angle(np.pi * dangle + roi_angle)
     return torch.stack([gx, gy, gw, gh, ga], dim=-1).view_as(deltas)
+
+
+def rotated_box_to_poly(rrects):
+    """(n,5) [x_ctr,y_ctr,w,h,angle] -> (n,8) corner polygon   (box_ops.py:592-613)"""
+    n = rrects.shape[0]
+    if n == 0:
+        return torch.zeros((0, 8), dtype=rrects.dtype, device=rrects.device)
+    x_ctr, y_ctr, width, height, angle = rrects[:, 0], rrects[:, 1], rrects[:, 2], rrects[:, 3], rrects[:, 4]
+    tl_x, tl_y, br_x, br_y = -width / 2, -height / 2, width / 2, height / 2
+    c, s = torch.cos(angle), torch.sin(angle)
+    xs = torch.stack([tl_x, br_x, br_x, tl_x], 1)
+    ys = torch.stack([tl_y, tl_y, br_y, br_y], 1)
+    px = c[:, None] * xs - s[:, None] * ys + x_ctr[:, None]
+    py = s[:, None] * xs + c[:, None] * ys + y_ctr[:, None]
+    return torch.stack([px, py], 2).reshape(n, 8)

@@ -1,1 +1,1 @@
-from .s2anet_head import AlignConv, bbox_decode  # noqa: F401
+from .s2anet_head import AlignConv, S2ANetHead, bbox_decode  # noqa: F401

@@ -101,3 +101,116 @@ class AlignConv(nn.Module):
                            dc.deformable_groups, _relu=True)
 
     execute = forward
+
+
+class _ConvReLU(nn.Sequential):
+    """ConvModule(conv 3x3 + ReLU) as S2ANet builds it (no norm)."""
+
+    def __init__(self, cin, cout):
+        super().__init__(nn.Conv2d(cin, cout, 3, stride=1, padding=1), nn.ReLU())
+        self.conv = self[0]
+
+
+class S2ANetHead(nn.Module):
+    """Forward-only (inference) restatement of S2ANetHead (s2anet_head.py:20-252, 510-601): the real caller of
+    bbox_decode -> AlignConv -> ORConv2d/RotationInvariantPooling -> multiclass_nms_rotated.  Batched where the
+    reference loops over images in Python; losses / target assignment are out of scope."""
+
+    def __init__(self, num_classes, in_channels, feat_channels=256, stacked_convs=2, with_orconv=True, anchor_scales=[4],
+                 anchor_ratios=[1.0], anchor_strides=[8, 16, 32, 64, 128], anchor_base_sizes=None,
+                 target_means=(.0, .0, .0, .0, .0), target_stds=(1.0, 1.0, 1.0, 1.0, 1.0),
+                 test_cfg=dict(nms_pre=2000, min_bbox_size=0, score_thr=0.05, nms=dict(type='nms_rotated', iou_thr=0.1),
+                               max_per_img=2000)):
+        super().__init__()
+        from ...ops.orn import ORConv2d, RotationInvariantPooling
+        from ..boxes.anchor_generator import AnchorGeneratorRotatedS2ANet
+        self.num_classes, self.in_channels, self.feat_channels = num_classes, in_channels, feat_channels
+        self.stacked_convs, self.with_orconv = stacked_convs, with_orconv
+        self.anchor_strides = list(anchor_strides)
+        self.anchor_base_sizes = list(anchor_strides) if anchor_base_sizes is None else anchor_base_sizes
+        self.target_means, self.target_stds = target_means, target_stds
+        self.cls_out_channels = num_classes - 1            # sigmoid classification (FocalLoss config)
+        self.test_cfg = test_cfg
+        self.anchor_generators = [AnchorGeneratorRotatedS2ANet(b, anchor_scales, anchor_ratios) for b in self.anchor_base_sizes]
+        self.base_anchors = dict()
+        self.fam_reg_convs = nn.ModuleList(_ConvReLU(in_channels if i == 0 else feat_channels, feat_channels)
+                                           for i in range(stacked_convs))
+        self.fam_reg = nn.Conv2d(feat_channels, 5, 1)
+        self.align_conv = AlignConv(feat_channels, feat_channels, kernel_size=3)
+        if with_orconv:
+            self.or_conv = ORConv2d(feat_channels, int(feat_channels / 8), kernel_size=3, padding=1, arf_config=(1, 8))
+        else:
+            self.or_conv = nn.Conv2d(feat_channels, feat_channels, 3, padding=1)
+        self.or_pool = RotationInvariantPooling(256, 8)
+        self.odm_reg_convs = nn.ModuleList(_ConvReLU(feat_channels, feat_channels) for _ in range(stacked_convs))
+        self.odm_cls_convs = nn.ModuleList(
+            _ConvReLU(int(feat_channels / 8) if i == 0 and with_orconv else feat_channels, feat_channels)
+            for i in range(stacked_convs))
+        self.odm_cls = nn.Conv2d(feat_channels, self.cls_out_channels, 3, padding=1)
+        self.odm_reg = nn.Conv2d(feat_channels, 5, 3, padding=1)
+        self.init_weights()
+
+    def init_weights(self):
+        import math
+        bias_cls = float(-math.log((1 - 0.01) / 0.01))
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.normal_(m.weight, 0, 0.01)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+        nn.init.constant_(self.odm_cls.bias, bias_cls)
+        self.align_conv.init_weights()
+
+    @torch.no_grad()
+    def forward_single(self, x, stride):
+        f = x
+        for conv in self.fam_reg_convs:
+            f = conv(f)
+        fam_bbox_pred = self.fam_reg(f)
+        lvl = self.anchor_strides.index(stride)
+        size = tuple(fam_bbox_pred.shape[-2:])
+        key = (lvl, size, x.device)
+        if key not in self.base_anchors:
+            self.base_anchors[key] = self.anchor_generators[lvl].grid_anchors(size, stride, device=x.device)
+        refine_anchor = bbox_decode(fam_bbox_pred, self.base_anchors[key], self.target_means, self.target_stds)
+        align_feat = self.align_conv(x, refine_anchor, stride)
+        or_feat = self.or_conv(align_feat)
+        reg_feat, cls_feat = or_feat, (self.or_pool(or_feat) if self.with_orconv else or_feat)
+        for conv in self.odm_reg_convs:
+            reg_feat = conv(reg_feat)
+        for conv in self.odm_cls_convs:
+            cls_feat = conv(cls_feat)
+        return fam_bbox_pred, refine_anchor, self.odm_cls(cls_feat), self.odm_reg(reg_feat)
+
+    @torch.no_grad()
+    def get_bboxes_single(self, cls_score_list, bbox_pred_list, mlvl_anchors, cfg=None):
+        from ...ops.nms_rotated import multiclass_nms_rotated
+        from ..boxes.box_ops import delta2bbox_rotated, rotated_box_to_poly
+        cfg = self.test_cfg if cfg is None else cfg
+        mlvl_bboxes, mlvl_scores = [], []
+        for cls_score, bbox_pred, anchors in zip(cls_score_list, bbox_pred_list, mlvl_anchors):
+            scores = cls_score.permute(1, 2, 0).reshape(-1, self.cls_out_channels).sigmoid()
+            bbox_pred = bbox_pred.permute(1, 2, 0).reshape(-1, 5)
+            anchors = anchors.reshape(-1, 5)
+            nms_pre = cfg.get('nms_pre', -1)
+            if nms_pre > 0 and scores.shape[0] > nms_pre:
+                _, topk_inds = scores.max(dim=1)[0].topk(nms_pre)
+                anchors, bbox_pred, scores = anchors[topk_inds], bbox_pred[topk_inds], scores[topk_inds]
+            mlvl_bboxes.append(delta2bbox_rotated(anchors, bbox_pred, self.target_means, self.target_stds))
+            mlvl_scores.append(scores)
+        mlvl_bboxes, mlvl_scores = torch.cat(mlvl_bboxes), torch.cat(mlvl_scores)
+        mlvl_scores = torch.cat([mlvl_scores.new_zeros((mlvl_scores.shape[0], 1)), mlvl_scores], dim=1)
+        det_bboxes, det_labels = multiclass_nms_rotated(mlvl_bboxes, mlvl_scores, cfg['score_thr'], cfg['nms'], cfg['max_per_img'])
+        return rotated_box_to_poly(det_bboxes[:, :5]), det_bboxes[:, 5], det_labels
+
+    @torch.no_grad()
+    def forward(self, feats):
+        """feats: list of (N,C,H_l,W_l) FPN maps -> list over images of (polys (k,8), scores (k,), labels (k,))."""
+        outs = [self.forward_single(x, s) for x, s in zip(feats, self.anchor_strides)]
+        num_imgs = feats[0].shape[0]
+        results = []
+        for i in range(num_imgs):
+            results.append(self.get_bboxes_single([o[2][i] for o in outs], [o[3][i] for o in outs], [o[1][i] for o in outs]))
+        return results
+
+    execute = forward

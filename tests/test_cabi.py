@@ -109,3 +109,38 @@ def test_box_coders_and_anchors_cpu():
     assert out.shape == (2, 6, 7, 5)
     one = delta2bbox_rotated(gen.grid_anchors((6, 7), 8), preds[1].permute(1, 2, 0).reshape(-1, 5), wh_ratio_clip=1e-6)
     assert torch.equal(out[1].reshape(-1, 5), one)
+
+
+def test_orn_arf_and_poly_cpu():
+    """active_rotating_filter against a loop restatement of ARF_forward_cpu_kernel (ops/orn.py:136-170);
+    rotated_box_to_poly against box_ops.py:568-590 (numpy); torch ops, so CPU is fine."""
+    import numpy as np
+    from jdet_b200.ops.orn import ORConv2d, RotationInvariantPooling, active_rotating_filter, arf_indices
+    from jdet_b200.models.boxes import rotated_box_to_poly
+    torch.manual_seed(0)
+    for (no, ni, nori, nrot) in ((4, 3, 1, 8), (2, 3, 8, 8), (3, 2, 4, 4)):
+        w, ind = torch.randn(no, ni, nori, 3, 3), arf_indices(nori, nrot, (3, 3))
+        got = active_rotating_filter(w, ind).numpy().ravel()
+        nE = nori * 9
+        want = np.zeros(no * nrot * ni * nE, np.float32)
+        wf, idf = w.numpy().ravel(), ind.numpy().ravel()
+        for i in range(no):
+            for j in range(ni):
+                for l in range(nE):
+                    for k in range(nrot):
+                        want[i * (nrot * ni * nE) + k * (ni * nE) + j * nE + int(idf[l * nrot + k]) - 1] = wf[i * ni * nE + j * nE + l]
+        assert np.array_equal(got, want)
+    m = ORConv2d(16, 4, 3, padding=1, arf_config=(1, 8))
+    y = m(torch.randn(2, 16, 8, 8))
+    assert y.shape == (2, 32, 8, 8) and RotationInvariantPooling(256, 8)(y).shape == (2, 4, 8, 8)
+    # rotation 0 of the ARF is the filter itself: the first of every 8 output channels is a plain conv with it
+    plain = torch.nn.functional.conv2d(torch.ones(1, 16, 5, 5), m.weight[:, :, 0], None, 1, 1)
+    assert torch.allclose(m(torch.ones(1, 16, 5, 5))[:, 0::8] - m.bias[0::8][None, :, None, None], plain, atol=1e-5)
+    r = np.array([[10, 20, 8, 4, 0.3], [0, 0, 2, 2, 0]], np.float32)
+    got = rotated_box_to_poly(torch.from_numpy(r)).numpy()
+    for b, p in zip(r, got):
+        x, y_, w, h, a = b
+        rect = np.array([[-w / 2, w / 2, w / 2, -w / 2], [-h / 2, -h / 2, h / 2, h / 2]])
+        R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        q = R.dot(rect)
+        assert np.allclose(p, np.stack([q[0] + x, q[1] + y_], 1).ravel(), atol=1e-5)

@@ -492,3 +492,53 @@ def test_roi_extractor_and_iou_calculator():
     b6 = np.concatenate([b, rng.random((50, 1)).astype(np.float32)], 1)
     assert np.array_equal(BboxOverlaps2D_rotated()(cu(b6), cu(b)).cpu().numpy(), oracle.box_iou_rotated(b, b, 0))
     assert np.array_equal(BboxOverlaps2D_rotated_v1()(cu(b), cu(b6)).cpu().numpy(), oracle.box_iou_rotated(b, b, 1))
+
+
+def test_s2anet_head_forward_against_oracle_ops():
+    """the forward-only S2ANetHead calls bbox_decode -> AlignConv -> ORConv2d/RIP -> multiclass NMS.
+    The same layers are re-run with the two hot-path ops swapped for their oracle restatements."""
+    from jdet_b200.models.roi_heads import S2ANetHead, bbox_decode
+    torch.manual_seed(3)
+    head = S2ANetHead(16, 256, test_cfg=dict(nms_pre=200, score_thr=0.3, nms=dict(type="nms_rotated", iou_thr=0.1),
+                                              max_per_img=100)).cuda().eval()
+    for m in head.modules():                       # the reference init (std 0.01) puts every score below score_thr
+        if isinstance(m, torch.nn.Conv2d):
+            torch.nn.init.normal_(m.weight, 0, 0.05)
+    torch.nn.init.normal_(head.or_conv.weight, 0, 0.05)
+    torch.nn.init.normal_(head.align_conv.deform_conv.weight, 0, 0.03)
+    torch.nn.init.constant_(head.odm_cls.bias, 0.0)
+    strides = head.anchor_strides
+    feats = [torch.randn(2, 256, 128 // s if 128 // s else 1, 128 // s if 128 // s else 1, device="cuda") for s in strides]
+    res = head(feats)
+    assert len(res) == 2
+    # per-level: AlignConv inside the head == oracle AlignConv on the same refined anchors
+    with torch.no_grad():
+        x, s0 = feats[0], strides[0]
+        f = x
+        for conv in head.fam_reg_convs:
+            f = conv(f)
+        anchors = head.anchor_generators[0].grid_anchors(tuple(x.shape[-2:]), s0, device=x.device)
+        refine = bbox_decode(head.fam_reg(f), anchors)
+        got = head.align_conv(x, refine, s0).cpu().numpy()
+    want = oracle.align_conv(x.cpu().numpy(), refine.cpu().numpy(), s0, head.align_conv.deform_conv.weight.detach().cpu().numpy())
+    assert np.abs(got - want).max() <= 5e-4          # |activations| ~ 10 with the inflated test weights
+    # final NMS inside the head == oracle multiclass NMS on the head's own pre-NMS boxes
+    outs = [head.forward_single(x, s) for x, s in zip(feats, strides)]
+    from jdet_b200.models.boxes import delta2bbox_rotated, rotated_box_to_poly
+    for i in range(2):
+        boxes, scores = [], []
+        for o in outs:
+            sc = o[2][i].permute(1, 2, 0).reshape(-1, 15).sigmoid()
+            bp, an = o[3][i].permute(1, 2, 0).reshape(-1, 5), o[1][i].reshape(-1, 5)
+            if sc.shape[0] > 200:
+                _, idx = sc.max(1)[0].topk(200)
+                sc, bp, an = sc[idx], bp[idx], an[idx]
+            boxes.append(delta2bbox_rotated(an, bp))
+            scores.append(sc)
+        boxes, scores = torch.cat(boxes), torch.cat(scores)
+        scores = torch.cat([scores.new_zeros((scores.shape[0], 1)), scores], 1)
+        wd, wl = oracle.multiclass_nms_rotated(boxes.cpu().numpy(), scores.cpu().numpy(), 0.3, dict(iou_thr=0.1), 100)
+        polys, sc, lab = res[i]
+        assert polys.shape == (wd.shape[0], 8) and wd.shape[0] > 0
+        assert np.array_equal(lab.cpu().numpy(), wl) and np.allclose(sc.cpu().numpy(), wd[:, 5])
+        assert np.allclose(polys.cpu().numpy(), rotated_box_to_poly(torch.from_numpy(wd[:, :5])).numpy(), atol=1e-3)
