@@ -108,7 +108,10 @@ class _ConvReLU(nn.Sequential):
 
     def __init__(self, cin, cout):
         super().__init__(nn.Conv2d(cin, cout, 3, stride=1, padding=1), nn.ReLU())
-        self.conv = self[0]
+
+    @property
+    def conv(self):
+        return self[0]
 
 
 class S2ANetHead(nn.Module):

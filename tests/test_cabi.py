@@ -144,3 +144,16 @@ def test_orn_arf_and_poly_cpu():
         R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
         q = R.dot(rect)
         assert np.allclose(p, np.stack([q[0] + x, q[1] + y_], 1).ravel(), atol=1e-5)
+
+
+def test_s2anet_head_wiring_cpu(monkeypatch):
+    """Layer wiring of the forward-only S2ANetHead (s2anet_head.py:207-252) with AlignConv stubbed out (no GPU here):
+    FAM regression -> refined anchors -> [AlignConv] -> ORConv2d -> (pooled) cls / reg towers."""
+    import torch
+    import jdet_b200.models.roi_heads.s2anet_head as H
+    monkeypatch.setattr(H.AlignConv, "forward", lambda self, x, anchors, stride: x)
+    head = H.S2ANetHead(16, 256, test_cfg=dict(nms_pre=200, score_thr=0.3, nms=dict(iou_thr=0.1), max_per_img=100)).eval()
+    assert len(list(head.fam_reg_convs[0].children())) == 2          # conv + relu, nothing applied twice
+    fam, refine, cls, reg = head.forward_single(torch.randn(2, 256, 16, 16), 8)
+    assert fam.shape == (2, 5, 16, 16) and refine.shape == (2, 16, 16, 5)
+    assert cls.shape == (2, 15, 16, 16) and reg.shape == (2, 5, 16, 16)
