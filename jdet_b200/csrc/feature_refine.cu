@@ -202,94 +202,103 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-template <int POINTS>
-__global__ void __launch_bounds__(1024) feature_refine_tma_kernel(const float* __restrict__ feat, const float* __restrict__ boxes,
-                                                                   int C, int H, int W, float spatial_scale, int rows_per_band,
-                                                                   int ch_per_cta, int stages, float* __restrict__ out) {
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumers = kConsumerWarps * 32;
+constexpr int kPPT = 4;                            // pixels per consumer thread
+constexpr int kBandPixels = kConsumers * kPPT;     // 1024
+
+// points = 1.  CTA = 8 consumer warps + 1 producer warp; grid = (row bands, channel chunks, N).
+// A band is kBandPixels / W full-width rows (+ kHalo rows either side): contiguous in an NCHW plane, so one
+// cp.async.bulk per channel stages it.  The producer lane only waits on empty[] and issues copies; the
+// consumers never block on a refill, and `stages` channels per CTA x several CTAs per SM are in flight.
+// Each consumer thread owns kPPT pixels (same column group, rows kConsumers/W apart): taps and weights live
+// in registers for the whole channel walk; a pixel whose taps leave the staged rows reads them from global.
+__global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_kernel(const float* __restrict__ feat,
+                                                                             const float* __restrict__ boxes, int C, int H,
+                                                                             int W, float spatial_scale, int rows_per_band,
+                                                                             int ch_per_cta, int stages, float* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = H * W;
   const int n = blockIdx.z;
   const int c0 = blockIdx.y * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
   const int r0 = blockIdx.x * rows_per_band;                       // first output row of this band
   const int lo = max(0, r0 - kHalo), hi = min(H, r0 + rows_per_band + kHalo);   // staged rows [lo, hi)
-  const int band_elems = (hi - lo) * W;
-  const uint32_t band_bytes = (uint32_t)band_elems * 4u;
+  const uint32_t band_bytes = (uint32_t)((hi - lo) * W) * 4u;
   const int stage_elems = (rows_per_band + 2 * kHalo) * W;
   float* ring = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * stage_elems);
   uint64_t* empty = full + kMaxStages;
-  const int tid = threadIdx.x, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int nch = c1 - c0;
 
   if (tid == 0) {
-    for (int s = 0; s < stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarps); }
+    for (int s = 0; s < stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const float* src0 = feat + ((size_t)n * C + c0) * HW + (size_t)lo * W;
-  if (tid == 0) {
-    for (int s = 0; s < stages && s < nch; s++) {
-      mbar_expect_tx(&full[s], band_bytes);
-      bulk_g2s(ring + (size_t)s * stage_elems, src0 + (size_t)s * HW, band_bytes, &full[s]);
+
+  if (tid >= kConsumers) {                                         // ---- producer warp
+    if (lane == 0) {
+      const float* src0 = feat + ((size_t)n * C + c0) * HW + (size_t)lo * W;
+      uint32_t stage = 0, phase = 0;
+      for (int c = 0; c < nch; c++) {
+        if (c >= stages) mbar_wait(&empty[stage], phase ^ 1);      // consumers released the previous occupant
+        mbar_expect_tx(&full[stage], band_bytes);
+        bulk_g2s(ring + (size_t)stage * stage_elems, src0 + (size_t)c * HW, band_bytes, &full[stage]);
+        if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+      }
     }
+    return;
   }
 
-  // this thread's pixel and its taps (band-relative offsets when every corner is staged)
-  const int row = r0 + tid / W, col = tid - (tid / W) * W;
-  const bool active = tid < rows_per_band * W && row < H;
-  const int p = row * W + col;
-  Tap4 taps[POINTS];
-  bool staged[POINTS];
-  if (active) {
-    const float* bb = boxes + ((size_t)n * HW + p) * 5;
-    const float roi_y = __fmul_rn(__ldg(bb), spatial_scale), roi_x = __fmul_rn(__ldg(bb + 1), spatial_scale);
-    taps[0] = fr_tap(roi_y, roi_x, H, W);
-    if (POINTS > 1) {
-      const float rw = __fmul_rn(__ldg(bb + 2), spatial_scale), rh = __fmul_rn(__ldg(bb + 3), spatial_scale), ra = __ldg(bb + 4);
-      const float w2 = rw * 0.5f, h2 = rh * 0.5f;
-      const float ca = cosf(ra), sa = sinf(ra);
-      const float wx = __fmul_rn(ca, w2), wy = __fmul_rn(sa, w2), hx = __fmul_rn(-sa, h2), hy = __fmul_rn(ca, h2);
-      taps[1 % POINTS] = fr_tap(__fadd_rn(__fadd_rn(roi_y, wy), hy), __fadd_rn(__fadd_rn(roi_x, wx), hx), H, W);
-      taps[2 % POINTS] = fr_tap(__fadd_rn(__fsub_rn(roi_y, wy), hy), __fadd_rn(__fsub_rn(roi_x, wx), hx), H, W);
-      taps[3 % POINTS] = fr_tap(__fsub_rn(__fsub_rn(roi_y, wy), hy), __fsub_rn(__fsub_rn(roi_x, wx), hx), H, W);
-      taps[4 % POINTS] = fr_tap(__fsub_rn(__fadd_rn(roi_y, wy), hy), __fsub_rn(__fadd_rn(roi_x, wx), hx), H, W);
-    }
-    const int blo = lo * W, bhi = hi * W;
+  // ---- consumers: this thread's pixels and their taps (band-relative offsets when every corner is staged)
+  Tap4 taps[kPPT];
+  int pc[kPPT];                                                    // centre, band-relative; -1: pixel not in the map
+  bool staged[kPPT];
+  const int blo = lo * W, bhi = hi * W;
+  const int band_px = min(rows_per_band, H - r0) * W;
 #pragma unroll
-    for (int i = 0; i < POINTS; i++) {
-      Tap4& t = taps[i];
-      staged[i] = t.o00 >= 0 && t.o00 >= blo && t.o11 < bhi;       // o00 is the smallest, o11 the largest offset
-      if (staged[i]) { t.o00 -= blo; t.o01 -= blo; t.o10 -= blo; t.o11 -= blo; }
+  for (int j = 0; j < kPPT; j++) {
+    const int i = tid + j * kConsumers;                            // pixel index inside the band
+    pc[j] = -1;
+    staged[j] = false;
+    taps[j].o00 = -1;
+    if (i < band_px) {
+      const int p = r0 * W + i;
+      const float* bb = boxes + ((size_t)n * HW + p) * 5;
+      Tap4 t = fr_tap(__fmul_rn(__ldg(bb), spatial_scale), __fmul_rn(__ldg(bb + 1), spatial_scale), H, W);
+      staged[j] = t.o00 >= blo && t.o11 < bhi;                     // o00 is the smallest, o11 the largest offset
+      if (staged[j]) { t.o00 -= blo; t.o01 -= blo; t.o10 -= blo; t.o11 -= blo; }
+      taps[j] = t;
+      pc[j] = p - blo;
     }
   }
-  const int pc = p - lo * W;                                       // centre, band-relative
-  float* dst = out + ((size_t)n * C + c0) * HW + p;
+  float* dst = out + ((size_t)n * C + c0) * HW + blo;
   const float* gplane = feat + ((size_t)n * C + c0) * HW;
 
   uint32_t stage = 0, phase = 0;
   for (int c = 0; c < nch; c++) {
     mbar_wait(&full[stage], phase);
     const float* sp = ring + (size_t)stage * stage_elems;
-    if (active) {
-      float v = sp[pc];
+    float v[kPPT];
 #pragma unroll
-      for (int i = 0; i < POINTS; i++) {
-        const Tap4& t = taps[i];
-        if (staged[i]) v += t.w1 * sp[t.o00] + t.w2 * sp[t.o01] + t.w3 * sp[t.o10] + t.w4 * sp[t.o11];
+    for (int j = 0; j < kPPT; j++) {
+      const Tap4& t = taps[j];
+      v[j] = 0.f;
+      if (pc[j] >= 0) {
+        v[j] = sp[pc[j]];
+        if (staged[j]) v[j] += t.w1 * sp[t.o00] + t.w2 * sp[t.o01] + t.w3 * sp[t.o10] + t.w4 * sp[t.o11];
         else if (t.o00 >= 0)
-          v += t.w1 * __ldg(gplane + t.o00) + t.w2 * __ldg(gplane + t.o01) + t.w3 * __ldg(gplane + t.o10) + t.w4 * __ldg(gplane + t.o11);
+          v[j] += t.w1 * __ldg(gplane + t.o00) + t.w2 * __ldg(gplane + t.o01) + t.w3 * __ldg(gplane + t.o10) + t.w4 * __ldg(gplane + t.o11);
       }
-      st_stream(dst, v);
     }
+#pragma unroll
+    for (int j = 0; j < kPPT; j++)
+      if (pc[j] >= 0) st_stream(dst + pc[j], v[j]);
+    __syncwarp();                                                  // every lane issued its stores, so its smem reads returned
+    if (lane == 0) mbar_arrive(&empty[stage]);
     dst += HW;
     gplane += HW;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[stage]);
-    if (tid == 0 && c + stages < nch) {                            // refill this slot with channel c + stages
-      mbar_wait(&empty[stage], phase);
-      mbar_expect_tx(&full[stage], band_bytes);
-      bulk_g2s(ring + (size_t)stage * stage_elems, src0 + (size_t)(c + stages) * HW, band_bytes, &full[stage]);
-    }
     if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
   }
 }
@@ -309,30 +318,24 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W;
   // TMA-staged path: full-width row bands (contiguous in NCHW), one thread per pixel of the band
-  if (W % 4 == 0 && W <= 1024 && ((uintptr_t)features & 15) == 0) {
+  // (measured on B200, cfg4: points=1 TMA ring 0.196 ms vs vec4 gather 0.203 ms; points=5 TMA ring 0.82 ms vs
+  //  register gather 0.68 ms — five sample sets per pixel make the smem tap reads, not the global stream, the cost)
+  if (points == 1 && W % 4 == 0 && W <= fr_tma::kBandPixels && ((uintptr_t)features & 15) == 0) {
     using namespace fr_tma;
-    const int max_threads = points == 1 ? 1024 : 512;
-    const int rows = max(1, min(H, max_threads / W));
-    const int threads = jdet_align_up((size_t)rows * W, 32);
+    const int rows = max(1, min(H, kBandPixels / W));
     const int stage_elems = (rows + 2 * kHalo) * W;
-    int stages = (int)((150 * 1024) / ((size_t)stage_elems * 4));
+    int stages = (int)((64 * 1024) / ((size_t)stage_elems * 4));   // ~64 KB of copies in flight per CTA, 3 CTAs per SM
     stages = stages > kMaxStages ? kMaxStages : stages;
     if (stages >= 2) {
       const int bands = jdet_ceil_div(H, rows);
       int cpc = C;
-      while (cpc > 4 * stages && (long long)bands * jdet_ceil_div(C, cpc) * N < 148 * 2) cpc = (cpc + 1) / 2;
+      while (cpc > 4 * stages && (long long)bands * jdet_ceil_div(C, cpc) * N < 148 * 6) cpc = (cpc + 1) / 2;
       const size_t smem = (size_t)stages * stage_elems * 4 + 2 * kMaxStages * sizeof(uint64_t);
       dim3 g(bands, jdet_ceil_div(C, cpc), N);
-      if (points == 1) {
-        JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // without this the driver picks the smallest carve-out that fits ONE block (ncu: occupancy_limit_shared_mem = 1)
-        JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        feature_refine_tma_kernel<1><<<g, threads, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output);
-      } else {
-        JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        feature_refine_tma_kernel<5><<<g, threads, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output);
-      }
+      JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      // without this the driver picks the smallest carve-out that fits ONE block (ncu: occupancy_limit_shared_mem = 1)
+      JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      feature_refine_tma_kernel<<<g, kConsumers + 32, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output);
       return (int)cudaGetLastError();
     }
   }

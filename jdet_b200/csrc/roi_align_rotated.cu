@@ -22,6 +22,7 @@
 //
 // Layout in HBM: input (B,C,H,W) fp32; rois (R,6) = [batch, cx, cy, w, h, theta]; output
 // (R,C,PH,PW) fp32; workspace: channel-last copy (B*H*W*C fp32) for the staged path.
+#include <algorithm>
 #include "common.cuh"
 
 namespace jdet {
@@ -108,61 +109,170 @@ __device__ __forceinline__ SampleTap make_tap(const RoiGeom& g, int ph, int pw, 
 
 void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cudaStream_t st);   // relayout.cu
 
+// ---- per-RoI tap table ---------------------------------------------------------------------------
+// A bin averages gh*gw samples of 4 taps each, but at DOTA RoI sizes the samples of one bin sit closer
+// than a pixel, so the 16 taps of a bin name only ~8 distinct pixels (cfg2: 767 taps -> 382 distinct
+// per RoI).  The table is built in two parallel passes:
+//   pass 1  one thread per sample: raw[4*sample + tap] = (pixel | -1, weight)
+//   pass 2  one lane per slot, a bin's slots in one lane group (tpb = 4*gh*gw a power of two <= 32):
+//           match.any finds the lanes naming the same pixel; the lowest becomes the pixel's leader and
+//           sums the group's weights in ascending slot order (deterministic); a ballot compacts the
+//           leaders to the front of fin[bin*tpb ..] and cnt[bin] counts them.  The tail is (-1, 0).
+//           Other grid sizes only drop the out-of-range samples (no merging).
+// Ends with a barrier; raw may be reused afterwards.
+template <int VERSION>
+__device__ __forceinline__ void build_tap_table(const RoiGeom& g, int nbins, int PW, int H, int W, int2* raw, int2* fin,
+                                                int* cnt) {
+  const int spb = g.gh * g.gw, tpb = 4 * spb;
+  for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
+    const int bin = s / spb, k = s - bin * spb;
+    const SampleTap t = make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
+    int4* dst = reinterpret_cast<int4*>(raw + 4 * s);
+    dst[0] = make_int4(t.o00, __float_as_int(t.w1), t.o01, __float_as_int(t.w2));
+    dst[1] = make_int4(t.o10, __float_as_int(t.w3), t.o11, __float_as_int(t.w4));
+  }
+  __syncthreads();
+  if (tpb <= 32 && (tpb & (tpb - 1)) == 0 && (blockDim.x & 31) == 0) {
+    const int lane = threadIdx.x & 31, gpw = 32 / tpb;            // lane groups (bins) per warp
+    const int sl = lane & (tpb - 1), grp = lane / tpb;
+    const unsigned gm = (tpb == 32 ? 0xffffffffu : ((1u << tpb) - 1u)) << (grp * tpb);
+    const unsigned below = (1u << lane) - 1u;
+    for (int bin0 = (threadIdx.x >> 5) * gpw; bin0 < nbins; bin0 += (blockDim.x >> 5) * gpw) {
+      const int bin = bin0 + grp;
+      const bool in = bin < nbins;
+      const int2* rb = raw + (in ? bin : 0) * tpb;
+      const int2 me = in ? rb[sl] : make_int2(-1, 0);
+      const unsigned m = __match_any_sync(0xffffffffu, me.x) & gm;
+      const bool leader = me.x >= 0 && (__ffs(m) - 1) == lane;
+      float wsum = 0.f;
+      if (leader)
+        for (unsigned mm = m; mm; mm &= mm - 1) wsum += __int_as_float(rb[(__ffs(mm) - 1) & (tpb - 1)].y);
+      const unsigned lb = __ballot_sync(0xffffffffu, leader) & gm;
+      const int nlead = __popc(lb);
+      const int pos = leader ? __popc(lb & below) : nlead + __popc(~lb & gm & below);
+      if (in) {
+        fin[bin * tpb + pos] = leader ? make_int2(me.x, __float_as_int(wsum)) : make_int2(-1, 0);
+        if (sl == 0) cnt[bin] = nlead;
+      }
+    }
+  } else {
+    for (int bin = threadIdx.x; bin < nbins; bin += blockDim.x) {
+      int n = 0;
+      for (int j = 0; j < tpb; j++) {
+        const int2 e = raw[bin * tpb + j];
+        if (e.x >= 0) fin[bin * tpb + n++] = e;
+      }
+      cnt[bin] = n;
+      for (; n < tpb; n++) fin[bin * tpb + n] = make_int2(-1, 0);
+    }
+  }
+  __syncthreads();
+}
+
 // ---- staged gather kernel ----------------------------------------------------------------------
-// grid = (R, C/SLAB slabs); 256 threads.  Requires C % 64 == 0 and PH*PW*gh*gw <= kMaxSamples
-// (sampling_ratio > 0).  Thread task = (bin, channel quad): SLAB/4 lanes span the slab's channels.
-template <int VERSION, int SLAB>
+// grid = (R, C / SLAB), SLAB = 4*QL*NQ channels; 256 threads.  Requires sampling_ratio > 0 and
+// PH*PW*gh*gw <= kMaxSamples.  QL lanes span a bin's channels (QL = 32: one bin per warp, every tap is
+// 512 contiguous bytes of one channel-last pixel); each lane owns NQ channel quads 128 channels apart,
+// so one table lookup + one address feed NQ 16-B loads.  With C = 256 a CTA is a whole RoI: the table is
+// built once per RoI.  The output slab (SLAB x PH*PW, contiguous in (R,C,PH,PW)) is assembled in smem
+// and leaves as 16-B streaming stores.
+template <int VERSION, int QL, int NQ>
 __global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const float* __restrict__ feat_nhwc,
                                                               const float* __restrict__ rois, int C, int H, int W,
                                                               int PH, int PW, float spatial_scale, int sample_num,
                                                               float* __restrict__ out) {
+  constexpr int SLAB = 4 * QL * NQ;
   extern __shared__ __align__(16) unsigned char smem[];
   const int nbins = PH * PW;
   const int r = blockIdx.x, c0 = blockIdx.y * SLAB;
-  constexpr int QL = SLAB / 4;                      // lanes (channel quads) per bin
   __shared__ RoiGeom g;
   if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)r * 6, spatial_scale, sample_num, PH, PW);
   __syncthreads();
   const int spb = g.gh * g.gw;                       // samples per bin
-  SampleTap* taps = reinterpret_cast<SampleTap*>(smem);
-  float* s_out = reinterpret_cast<float*>(taps + nbins * spb);   // [SLAB][nbins]
-  for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
-    const int bin = s / spb, k = s - bin * spb;
-    taps[s] = make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
-  }
-  __syncthreads();
-  const float* base = feat_nhwc + (size_t)g.batch * H * W * C + c0;
-  const int q = threadIdx.x % QL;                   // channel quad within the slab
+  const int tpb = 4 * spb;                           // tap slots per bin
+  const int nslots = nbins * tpb;
+  const int S = nbins | 1;                           // odd row stride of s_out: see the store below
+  int2* fin = reinterpret_cast<int2*>(smem);         // [nslots] compacted (pixel, weight) lists
+  int* cnt = reinterpret_cast<int*>(fin + nslots);   // [nbins rounded up to 4]
+  int2* raw = reinterpret_cast<int2*>(cnt + ((nbins + 3) & ~3));   // [nslots], dead after the build: aliased by s_out
+  float* s_out = reinterpret_cast<float*>(raw);      // [SLAB][S]
+  build_tap_table<VERSION>(g, nbins, PW, H, W, raw, fin, cnt);
+
+  const int q = threadIdx.x % QL;                    // channel quad within a 128-channel group
+  const float* base = feat_nhwc + (size_t)g.batch * H * W * C + c0 + 4 * q;
+  const int icnt = (int)g.inv_count;
+  const bool pow2 = (icnt & (icnt - 1)) == 0;        // x / 2^k == x * 2^-k exactly
+  const float rcnt = 1.f / g.inv_count;
+  const int rot = (q >> 3) & 3;
   for (int bin = threadIdx.x / QL; bin < nbins; bin += blockDim.x / QL) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const SampleTap* tp = taps + bin * spb;
-    for (int k = 0; k < spb; k++) {
-      const SampleTap t = tp[k];
-      if (t.o00 < 0) continue;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o00 * C) + q);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o01 * C) + q);
-      const float4 c = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o10 * C) + q);
-      const float4 d = __ldg(reinterpret_cast<const float4*>(base + (size_t)t.o11 * C) + q);
-      acc.x += t.w1 * a.x + t.w2 * b.x + t.w3 * c.x + t.w4 * d.x;
-      acc.y += t.w1 * a.y + t.w2 * b.y + t.w3 * c.y + t.w4 * d.y;
-      acc.z += t.w1 * a.z + t.w2 * b.z + t.w3 * c.z + t.w4 * d.z;
-      acc.w += t.w1 * a.w + t.w2 * b.w + t.w3 * c.w + t.w4 * d.w;
+    float4 acc[NQ];
+#pragma unroll
+    for (int u = 0; u < NQ; u++) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int2* e = fin + bin * tpb;
+    const int n = cnt[bin];
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {                     // 4*NQ independent 16-B loads in flight
+      const int4 e01 = *reinterpret_cast<const int4*>(e + k), e23 = *reinterpret_cast<const int4*>(e + k + 2);
+      const float* p0 = base + (size_t)e01.x * C;
+      const float* p1 = base + (size_t)e01.z * C;
+      const float* p2 = base + (size_t)e23.x * C;
+      const float* p3 = base + (size_t)e23.z * C;
+      float4 v0[NQ], v1[NQ], v2[NQ], v3[NQ];
+#pragma unroll
+      for (int u = 0; u < NQ; u++) {
+        v0[u] = __ldg(reinterpret_cast<const float4*>(p0 + 4 * QL * u));
+        v1[u] = __ldg(reinterpret_cast<const float4*>(p1 + 4 * QL * u));
+        v2[u] = __ldg(reinterpret_cast<const float4*>(p2 + 4 * QL * u));
+        v3[u] = __ldg(reinterpret_cast<const float4*>(p3 + 4 * QL * u));
+      }
+      const float w0 = __int_as_float(e01.y), w1 = __int_as_float(e01.w);
+      const float w2 = __int_as_float(e23.y), w3 = __int_as_float(e23.w);
+#pragma unroll
+      for (int u = 0; u < NQ; u++) {
+        acc[u].x += w0 * v0[u].x + w1 * v1[u].x + w2 * v2[u].x + w3 * v3[u].x;
+        acc[u].y += w0 * v0[u].y + w1 * v1[u].y + w2 * v2[u].y + w3 * v3[u].y;
+        acc[u].z += w0 * v0[u].z + w1 * v1[u].z + w2 * v2[u].z + w3 * v3[u].z;
+        acc[u].w += w0 * v0[u].w + w1 * v1[u].w + w2 * v2[u].w + w3 * v3[u].w;
+      }
     }
-    const float cnt = g.inv_count;
-    s_out[(4 * q + 0) * nbins + bin] = acc.x / cnt;
-    s_out[(4 * q + 1) * nbins + bin] = acc.y / cnt;
-    s_out[(4 * q + 2) * nbins + bin] = acc.z / cnt;
-    s_out[(4 * q + 3) * nbins + bin] = acc.w / cnt;
+    for (; k < n; k++) {
+      const int2 t = e[k];
+      const float* p = base + (size_t)t.x * C;
+      const float w = __int_as_float(t.y);
+#pragma unroll
+      for (int u = 0; u < NQ; u++) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + 4 * QL * u));
+        acc[u].x += w * v.x; acc[u].y += w * v.y; acc[u].z += w * v.z; acc[u].w += w * v.w;
+      }
+    }
+    // s_out[channel][bin], row stride S odd.  A lane's 4 channels are 4 rows apart from its neighbour's, so
+    // a plain store would hit 8 banks 4 lanes deep; lanes 8 apart instead store their components in a
+    // rotated order (rot = lane/8), which spreads every store instruction over all 32 banks.
+#pragma unroll
+    for (int u = 0; u < NQ; u++) {
+      float4 a = acc[u];
+      if (pow2) { a.x *= rcnt; a.y *= rcnt; a.z *= rcnt; a.w *= rcnt; }
+      else { a.x /= g.inv_count; a.y /= g.inv_count; a.z /= g.inv_count; a.w /= g.inv_count; }
+      const float b0 = rot & 1 ? a.y : a.x, b1 = rot & 1 ? a.z : a.y, b2 = rot & 1 ? a.w : a.z, b3 = rot & 1 ? a.x : a.w;
+      const float d0 = rot & 2 ? b2 : b0, d1 = rot & 2 ? b3 : b1, d2 = rot & 2 ? b0 : b2, d3 = rot & 2 ? b1 : b3;
+      float* row = s_out + (size_t)(4 * QL * u + 4 * q) * S + bin;     // d_j is component (j + rot) & 3
+      row[((0 + rot) & 3) * S] = d0;
+      row[((1 + rot) & 3) * S] = d1;
+      row[((2 + rot) & 3) * S] = d2;
+      row[((3 + rot) & 3) * S] = d3;
+    }
   }
   __syncthreads();
   // out[r][c0 .. c0+SLAB-1][bins] is one contiguous run of SLAB*nbins floats
   float* dst = out + ((size_t)r * C + c0) * nbins;
   const int total = SLAB * nbins;
-  if ((total & 3) == 0 && ((((size_t)r * C + c0) * nbins) & 3) == 0) {
-    for (int i = threadIdx.x * 4; i < total; i += blockDim.x * 4)
-      st_stream_v4(dst + i, s_out[i], s_out[i + 1], s_out[i + 2], s_out[i + 3]);
+  if (S == nbins && (total & 3) == 0 && ((((size_t)r * C + c0) * nbins) & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < total; i += blockDim.x * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(s_out + i);
+      st_stream_v4(dst + i, v.x, v.y, v.z, v.w);
+    }
   } else {
-    for (int i = threadIdx.x; i < total; i += blockDim.x) st_stream(dst + i, s_out[i]);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) st_stream(dst + i, s_out[(i / nbins) * S + i % nbins]);
   }
 }
 
@@ -237,32 +347,27 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nhwc_kernel(const float* __
   if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)r * 6, spatial_scale, sample_num, PH, PW);
   __syncthreads();
   const int spb = g.gh * g.gw;
-  SampleTap* taps = reinterpret_cast<SampleTap*>(smem);
-  float* s_go = reinterpret_cast<float*>(taps + nbins * spb);   // [SLAB][nbins], as laid out in grad_out
-  for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
-    const int bin = s / spb, k = s - bin * spb;
-    taps[s] = make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
-  }
+  const int tpb = 4 * spb, nslots = nbins * tpb;
+  int2* fin = reinterpret_cast<int2*>(smem);
+  int2* raw = fin + nslots;
+  float* s_go = reinterpret_cast<float*>(raw + nslots);         // [SLAB][nbins], as laid out in grad_out
+  int* cnt = reinterpret_cast<int*>(s_go + SLAB * nbins);
   const float* src = grad_out + ((size_t)r * C + c0) * nbins;
   for (int i = threadIdx.x; i < SLAB * nbins; i += blockDim.x) s_go[i] = __ldg(src + i);
-  __syncthreads();
+  build_tap_table<VERSION>(g, nbins, PW, H, W, raw, fin, cnt);  // one atomic per distinct pixel of a bin
   float* base = grad_nhwc + (size_t)g.batch * H * W * C + c0;
   const int q = threadIdx.x % QL;
-  const float cnt = (float)spb;                      // the backward divides by gh*gw in both versions
+  const float cntf = (float)spb;                     // the backward divides by gh*gw in both versions
   for (int bin = threadIdx.x / QL; bin < nbins; bin += blockDim.x / QL) {
     const float4 go = make_float4(s_go[(4 * q + 0) * nbins + bin], s_go[(4 * q + 1) * nbins + bin],
                                   s_go[(4 * q + 2) * nbins + bin], s_go[(4 * q + 3) * nbins + bin]);
-    const SampleTap* tp = taps + bin * spb;
-    for (int k = 0; k < spb; k++) {
-      const SampleTap t = tp[k];
-      if (t.o00 < 0) continue;
-      const int o[4] = {t.o00, t.o01, t.o10, t.o11};
-      const float w[4] = {t.w1, t.w2, t.w3, t.w4};
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const float4 v = make_float4(go.x * w[j] / cnt, go.y * w[j] / cnt, go.z * w[j] / cnt, go.w * w[j] / cnt);
-        atomicAdd(reinterpret_cast<float4*>(base + (size_t)o[j] * C) + q, v);
-      }
+    const int2* e = fin + bin * tpb;
+    const int n = cnt[bin];
+    for (int k = 0; k < n; k++) {
+      const int2 t = e[k];
+      const float w = __int_as_float(t.y);
+      const float4 v = make_float4(go.x * w / cntf, go.y * w / cntf, go.z * w / cntf, go.w * w / cntf);
+      atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.x * C) + q, v);
     }
   }
 }
@@ -342,19 +447,20 @@ JDET_API int jdet_roi_align_rotated(int version, const float* input, int B, int 
     if (!workspace || workspace_bytes < need) return JDET_ERR_WORKSPACE;
     float* nhwc = (float*)workspace;
     launch_nchw_to_nhwc(input, nhwc, B, C, H * W, st);
-    const int slab = (C % 128 == 0) ? 128 : 64;      // 128: one bin per warp, 512 contiguous bytes per tap
-    const size_t smem = (size_t)nbins * sampling_ratio * sampling_ratio * sizeof(SampleTap) + (size_t)slab * nbins * 4;
+    const int slab = (C % 256 == 0) ? 256 : (C % 128 == 0) ? 128 : 64;
+    const size_t slot_bytes = (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2);
+    const size_t smem = slot_bytes + (size_t)((nbins + 3) & ~3) * 4 + std::max(slot_bytes, (size_t)slab * (nbins | 1) * 4);
     dim3 grid(R, C / slab);
-    // (measured alternatives on B200, cfg2: one CTA per RoI over all channels 163 us; per-bin tap merging
-    //  185-250 us; 64-channel slabs 146 us, with 128/192/64-thread CTAs 144/150/178 us; 128-channel slabs 136 us)
-#define JDET_LAUNCH_ROI(V, S)                                                                                          \
+    // (measured on B200, cfg2, same relayout: (RoI, 64-ch slab) CTAs with 16 undeduplicated taps 146 us; 128-ch
+    //  slabs 136 us; tap merging by a serial per-bin pass 185-250 us, by a parallel pass without compaction 147 us)
+#define JDET_LAUNCH_ROI(V, QL_, NQ_)                                                                                   \
   do {                                                                                                                 \
     if (smem > 48 * 1024)                                                                                              \
-      JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    roi_align_nhwc_kernel<V, S><<<grid, 256, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);          \
+      JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<V, QL_, NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    roi_align_nhwc_kernel<V, QL_, NQ_><<<grid, 256, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);        \
   } while (0)
-    if (version == 1) { if (slab == 128) JDET_LAUNCH_ROI(1, 128); else JDET_LAUNCH_ROI(1, 64); }
-    else              { if (slab == 128) JDET_LAUNCH_ROI(0, 128); else JDET_LAUNCH_ROI(0, 64); }
+    if (version == 1) { if (slab == 256) JDET_LAUNCH_ROI(1, 32, 2); else if (slab == 128) JDET_LAUNCH_ROI(1, 32, 1); else JDET_LAUNCH_ROI(1, 16, 1); }
+    else              { if (slab == 256) JDET_LAUNCH_ROI(0, 32, 2); else if (slab == 128) JDET_LAUNCH_ROI(0, 32, 1); else JDET_LAUNCH_ROI(0, 16, 1); }
 #undef JDET_LAUNCH_ROI
   } else {
     const int ch_per_cta = 32;
@@ -392,7 +498,7 @@ JDET_API int jdet_roi_align_rotated_backward(int version, const float* grad_outp
     float* nhwc = (float*)workspace;
     JDET_RETURN_IF_CUDA(cudaMemsetAsync(nhwc, 0, in_bytes, st));
     const int slab = (C % 128 == 0) ? 128 : 64;
-    const size_t smem = (size_t)nbins * sampling_ratio * sampling_ratio * sizeof(SampleTap) + (size_t)slab * nbins * 4;
+    const size_t smem = 2 * (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2) + (size_t)slab * nbins * 4 + (size_t)nbins * 4;
     dim3 grid(R, C / slab);
 #define JDET_LAUNCH_BWD(V, S)                                                                                          \
   do {                                                                                                                 \

@@ -225,6 +225,9 @@ def _rois(rng, R, B, extent, lo=8, hi=256):
 @pytest.mark.parametrize("cfg", [
     dict(B=2, C=64, H=40, W=56, R=300, out=(7, 7), sr=2, scale=0.25),      # staged (channel-last) path
     dict(B=1, C=128, H=32, W=32, R=200, out=(5, 3), sr=3, scale=0.125),    # staged, non-square bins
+    dict(B=1, C=256, H=24, W=24, R=150, out=(4, 4), sr=1, scale=0.25),     # staged, whole-RoI CTAs, 4 slots/bin, even bin count
+    dict(B=2, C=256, H=32, W=32, R=260, out=(6, 6), sr=2, scale=0.125),    # staged, even bin count (padded smem rows)
+    dict(B=1, C=128, H=20, W=20, R=120, out=(2, 2), sr=4, scale=0.25),     # staged, 64 slots/bin (no tap merging)
     dict(B=2, C=24, H=40, W=56, R=100, out=(7, 7), sr=2, scale=0.25),      # direct path (C % 64 != 0)
     dict(B=2, C=64, H=64, W=64, R=8, out=(7, 7), sr=2, scale=0.0625),      # direct path (few RoIs)
     dict(B=1, C=16, H=48, W=48, R=40, out=(7, 7), sr=0, scale=0.25),       # adaptive grid (sampling_ratio 0)
@@ -311,6 +314,7 @@ BWD_TOL = 2e-4   # float atomics: summation order differs from the fp64-accumula
 @pytest.mark.parametrize("cfg", [
     dict(B=2, C=64, H=40, W=56, R=300, out=(7, 7), sr=2, scale=0.25),      # staged: channel-last scratch + vector atomics
     dict(B=1, C=128, H=32, W=32, R=200, out=(5, 3), sr=3, scale=0.125),
+    dict(B=1, C=256, H=24, W=24, R=150, out=(4, 4), sr=1, scale=0.25),
     dict(B=2, C=24, H=40, W=56, R=60, out=(7, 7), sr=2, scale=0.25),       # direct NCHW atomics
     dict(B=1, C=16, H=48, W=48, R=30, out=(7, 7), sr=0, scale=0.25),       # adaptive grid
 ])
