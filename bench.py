@@ -342,6 +342,21 @@ def run_extra(torch, dist, ops, jdist, dev, rank, world, peaks, flush):
                      "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg}}
     del go
 
+    # cfg2 again with the FPN map already channel-last in memory (torch.channels_last): no re-layout pass
+    gcl = torch.Generator(device=dev).manual_seed(6 + rank)
+    fcl = torch.randn((1, 256, 256, 256), device=dev, generator=gcl).contiguous(memory_format=torch.channels_last)
+    fn = lambda: ops.roi_align_rotated_v1.roi_align(fcl, rois_b, (7, 7), 0.25, 2)
+    fn()
+    K = 30
+    ms = agg(time_steps(torch, fn, K, 3, flush)) / K
+    alg = fcl.numel() * 4 + rois_b.numel() * 4 + 2048 * 256 * 49 * 4
+    ex["roi_align_rotated_channels_last"] = {
+        "metric": "RoIs/s", "value": 2048 * world / (ms * 1e-3), "unit": "RoIs/s", "ms_per_step": ms, "steps": K,
+        "config": {"workload": "roi_align_rotated_v1 at cfg2, input handed over as a torch.channels_last tensor (jdet_roi_align_rotated_nhwc)"},
+        "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg}}
+    del fcl
+
     # cfg4: S2ANet-R50-FPN shapes, bs 8: feature_refine + AlignConv over the 5 levels
     levels = [(128, 8), (64, 16), (32, 32), (16, 64), (8, 128)]
     g = torch.Generator(device=dev).manual_seed(77 + rank)

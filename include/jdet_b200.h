@@ -65,6 +65,14 @@ int jdet_roi_align_rotated(int version, const float* input, int B, int C, int H,
                            int R, int PH, int PW, float spatial_scale, int sampling_ratio, float* output,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* same op for a feature map that is ALREADY channel-last in memory, (B,H,W,C) — e.g. a torch channels_last
+ * tensor out of the FPN convolutions: no re-layout pass; the workspace only holds the per-RoI tap tables.  Needs C % 64 == 0, sampling_ratio > 0 and
+ * PH*PW*sampling_ratio^2 <= 1024; otherwise JDET_ERR_UNSUPPORTED (callers fall back to the NCHW entry point). */
+size_t jdet_roi_align_rotated_nhwc_workspace_bytes(int R, int PH, int PW, int sampling_ratio);
+int jdet_roi_align_rotated_nhwc(int version, const float* input_nhwc, int B, int C, int H, int W, const float* rois,
+                                int R, int PH, int PW, float spatial_scale, int sampling_ratio, float* output,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* backward w.r.t. input — replaces: _RotatedROIAlign[_v1].grad ops/roi_align_rotated_v1.py:328-351 (kernel :192-298),
  * ops/roi_align_rotated.py:285-308 (kernel :164-255).  grad_output (R,C,PH,PW) -> grad_input (B,C,H,W), fully written. */
 size_t jdet_roi_align_rotated_backward_workspace_bytes(int B, int C, int H, int W, int R, int PH, int PW,

@@ -36,4 +36,19 @@ __device__ __forceinline__ void st_stream(float* p, float a) {
   asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
+// 16-B read-only load that yields zeros when !live.  volatile: a run of these stays a run of loads in the
+// emitted code (the compiler otherwise interleaves each load with its consumers to save registers, which
+// serialises the memory latency).
+__device__ __forceinline__ float4 ldg_v4_if(const float* p, bool live) {
+  float4 v;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.s32 q, %5, 0;\n\t"
+      "mov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "r"((int)live));
+  return v;
+}
+
 }  // namespace jdet

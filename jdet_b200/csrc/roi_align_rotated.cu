@@ -23,6 +23,7 @@
 // Layout in HBM: input (B,C,H,W) fp32; rois (R,6) = [batch, cx, cy, w, h, theta]; output
 // (R,C,PH,PW) fp32; workspace: channel-last copy (B*H*W*C fp32) for the staged path.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace jdet {
@@ -122,7 +123,9 @@ void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cuda
 // Ends with a barrier; raw may be reused afterwards.
 template <int VERSION>
 __device__ __forceinline__ void build_tap_table(const RoiGeom& g, int nbins, int PW, int H, int W, int2* raw, int2* fin,
-                                                int* cnt) {
+                                                int fstride, int* cnt) {
+  // fin holds fstride >= tpb (a multiple of 8) entries per bin: cnt[bin] merged taps, then (0, 0.f) entries, so a
+  // reader may run 8-wide steps whose tail needs a load predicate but no weight select.
   const int spb = g.gh * g.gw, tpb = 4 * spb;
   for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
     const int bin = s / spb, k = s - bin * spb;
@@ -151,127 +154,260 @@ __device__ __forceinline__ void build_tap_table(const RoiGeom& g, int nbins, int
       const int nlead = __popc(lb);
       const int pos = leader ? __popc(lb & below) : nlead + __popc(~lb & gm & below);
       if (in) {
-        fin[bin * tpb + pos] = leader ? make_int2(me.x, __float_as_int(wsum)) : make_int2(-1, 0);
+        int2* fb = fin + bin * fstride;
+        fb[pos] = leader ? make_int2(me.x, __float_as_int(wsum)) : make_int2(0, 0);
+        for (int i = tpb + sl; i < fstride; i += tpb) fb[i] = make_int2(0, 0);
         if (sl == 0) cnt[bin] = nlead;
       }
     }
   } else {
     for (int bin = threadIdx.x; bin < nbins; bin += blockDim.x) {
+      int2* fb = fin + bin * fstride;
       int n = 0;
       for (int j = 0; j < tpb; j++) {
         const int2 e = raw[bin * tpb + j];
-        if (e.x >= 0) fin[bin * tpb + n++] = e;
+        if (e.x >= 0) fb[n++] = e;
       }
       cnt[bin] = n;
-      for (; n < tpb; n++) fin[bin * tpb + n] = make_int2(-1, 0);
+      for (; n < fstride; n++) fb[n] = make_int2(0, 0);
     }
   }
   __syncthreads();
 }
 
-// ---- staged gather kernel ----------------------------------------------------------------------
-// grid = (R, C / SLAB), SLAB = 4*QL*NQ channels; 256 threads.  Requires sampling_ratio > 0 and
-// PH*PW*gh*gw <= kMaxSamples.  QL lanes span a bin's channels (QL = 32: one bin per warp, every tap is
-// 512 contiguous bytes of one channel-last pixel); each lane owns NQ channel quads 128 channels apart,
-// so one table lookup + one address feed NQ 16-B loads.  With C = 256 a CTA is a whole RoI: the table is
-// built once per RoI.  The output slab (SLAB x PH*PW, contiguous in (R,C,PH,PW)) is assembled in smem
-// and leaves as 16-B streaming stores.
-template <int VERSION, int QL, int NQ>
-__global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const float* __restrict__ feat_nhwc,
-                                                              const float* __restrict__ rois, int C, int H, int W,
-                                                              int PH, int PW, float spatial_scale, int sample_num,
-                                                              float* __restrict__ out) {
-  constexpr int SLAB = 4 * QL * NQ;
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int nbins = PH * PW;
-  const int r = blockIdx.x, c0 = blockIdx.y * SLAB;
-  __shared__ RoiGeom g;
-  if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)r * 6, spatial_scale, sample_num, PH, PW);
-  __syncthreads();
-  const int spb = g.gh * g.gw;                       // samples per bin
-  const int tpb = 4 * spb;                           // tap slots per bin
-  const int nslots = nbins * tpb;
-  const int S = nbins | 1;                           // odd row stride of s_out: see the store below
-  int2* fin = reinterpret_cast<int2*>(smem);         // [nslots] compacted (pixel, weight) lists
-  int* cnt = reinterpret_cast<int*>(fin + nslots);   // [nbins rounded up to 4]
-  int2* raw = reinterpret_cast<int2*>(cnt + ((nbins + 3) & ~3));   // [nslots], dead after the build: aliased by s_out
-  float* s_out = reinterpret_cast<float*>(raw);      // [SLAB][S]
-  build_tap_table<VERSION>(g, nbins, PW, H, W, raw, fin, cnt);
+// ---- prologue kernel: per-RoI tap tables (+ the NCHW -> channel-last re-layout) -------------------------
+// Table record of one RoI in the caller's workspace (16-B granular):
+//   int4 {batch, float bits of the divisor, fin entries per bin, 0} | int cnt[nbins rounded up to 4] | int2 fin[nbins][fstride]
+// Building it is latency-bound ALU work (double sincos, two barriers, match.any); the re-layout is an HBM
+// stream.  One launch does both, interleaved (see the kernel), so the gather CTAs start with nothing but loads
+// to do.
+__host__ __device__ inline int roi_table_fstride(int sampling_ratio) { return (4 * sampling_ratio * sampling_ratio + 7) & ~7; }
+__host__ __device__ inline size_t roi_table_stride(int nbins, int sampling_ratio) {
+  return 16 + (size_t)((nbins + 3) & ~3) * 4 + (size_t)nbins * roi_table_fstride(sampling_ratio) * sizeof(int2);
+}
 
-  const int q = threadIdx.x % QL;                    // channel quad within a 128-channel group
-  const float* base = feat_nhwc + (size_t)g.batch * H * W * C + c0 + 4 * q;
-  const int icnt = (int)g.inv_count;
-  const bool pow2 = (icnt & (icnt - 1)) == 0;        // x / 2^k == x * 2^-k exactly
-  const float rcnt = 1.f / g.inv_count;
-  const int rot = (q >> 3) & 3;
-  for (int bin = threadIdx.x / QL; bin < nbins; bin += blockDim.x / QL) {
-    float4 acc[NQ];
+__device__ __forceinline__ void relayout_tile(const float* __restrict__ in, float* __restrict__ out, int C, int HW, int b,
+                                              int p0, int c0, float (*tile)[33]) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const float* src = in + (size_t)b * C * HW;
+  float* dst = out + (size_t)b * C * HW;
 #pragma unroll
-    for (int u = 0; u < NQ; u++) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int2* e = fin + bin * tpb;
-    const int n = cnt[bin];
-    int k = 0;
-    for (; k + 4 <= n; k += 4) {                     // 4*NQ independent 16-B loads in flight
-      const int4 e01 = *reinterpret_cast<const int4*>(e + k), e23 = *reinterpret_cast<const int4*>(e + k + 2);
-      const float* p0 = base + (size_t)e01.x * C;
-      const float* p1 = base + (size_t)e01.z * C;
-      const float* p2 = base + (size_t)e23.x * C;
-      const float* p3 = base + (size_t)e23.z * C;
-      float4 v0[NQ], v1[NQ], v2[NQ], v3[NQ];
+  for (int k = 0; k < 4; k++) {
+    const int c = c0 + ty + 8 * k, p = p0 + tx;
+    if (c < C && p < HW) tile[ty + 8 * k][tx] = __ldg(src + (size_t)c * HW + p);
+  }
+  __syncthreads();
 #pragma unroll
-      for (int u = 0; u < NQ; u++) {
-        v0[u] = __ldg(reinterpret_cast<const float4*>(p0 + 4 * QL * u));
-        v1[u] = __ldg(reinterpret_cast<const float4*>(p1 + 4 * QL * u));
-        v2[u] = __ldg(reinterpret_cast<const float4*>(p2 + 4 * QL * u));
-        v3[u] = __ldg(reinterpret_cast<const float4*>(p3 + 4 * QL * u));
-      }
-      const float w0 = __int_as_float(e01.y), w1 = __int_as_float(e01.w);
-      const float w2 = __int_as_float(e23.y), w3 = __int_as_float(e23.w);
+  for (int k = 0; k < 4; k++) {
+    const int p = p0 + ty + 8 * k, c = c0 + tx;
+    if (c < C && p < HW) dst[(size_t)p * C + c] = tile[tx][ty + 8 * k];
+  }
+}
+
+// 32 channels x 128 pixels per CTA with 16-B global accesses on both sides (HW % 4 == 0, C % 4 == 0, 16-B aligned
+// bases): 4 independent loads per thread in flight and a quarter of the load/store instructions of the scalar
+// 32x32 tile, which is issue-bound (72 % issue slots busy at 5 TB/s).
+constexpr int kTileW = 128;
+__device__ __forceinline__ void relayout_tile_v4(const float* __restrict__ in, float* __restrict__ out, int C, int HW, int b,
+                                                 int p0, int c0, float (*tile)[kTileW + 1]) {
+  const float* src = in + (size_t)b * C * HW;
+  float* dst = out + (size_t)b * C * HW;
+  {
+    const int row = threadIdx.x >> 3, c = c0 + row;                // channel row
+    float4 v[4];
 #pragma unroll
-      for (int u = 0; u < NQ; u++) {
-        acc[u].x += w0 * v0[u].x + w1 * v1[u].x + w2 * v2[u].x + w3 * v3[u].x;
-        acc[u].y += w0 * v0[u].y + w1 * v1[u].y + w2 * v2[u].y + w3 * v3[u].y;
-        acc[u].z += w0 * v0[u].z + w1 * v1[u].z + w2 * v2[u].z + w3 * v3[u].z;
-        acc[u].w += w0 * v0[u].w + w1 * v1[u].w + w2 * v2[u].w + w3 * v3[u].w;
-      }
+    for (int i = 0; i < 4; i++) {
+      const int p = p0 + 4 * ((threadIdx.x & 7) + 8 * i);
+      v[i] = (c < C && p < HW) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)c * HW + p)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (; k < n; k++) {
-      const int2 t = e[k];
-      const float* p = base + (size_t)t.x * C;
-      const float w = __int_as_float(t.y);
 #pragma unroll
-      for (int u = 0; u < NQ; u++) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p + 4 * QL * u));
-        acc[u].x += w * v.x; acc[u].y += w * v.y; acc[u].z += w * v.z; acc[u].w += w * v.w;
-      }
-    }
-    // s_out[channel][bin], row stride S odd.  A lane's 4 channels are 4 rows apart from its neighbour's, so
-    // a plain store would hit 8 banks 4 lanes deep; lanes 8 apart instead store their components in a
-    // rotated order (rot = lane/8), which spreads every store instruction over all 32 banks.
-#pragma unroll
-    for (int u = 0; u < NQ; u++) {
-      float4 a = acc[u];
-      if (pow2) { a.x *= rcnt; a.y *= rcnt; a.z *= rcnt; a.w *= rcnt; }
-      else { a.x /= g.inv_count; a.y /= g.inv_count; a.z /= g.inv_count; a.w /= g.inv_count; }
-      const float b0 = rot & 1 ? a.y : a.x, b1 = rot & 1 ? a.z : a.y, b2 = rot & 1 ? a.w : a.z, b3 = rot & 1 ? a.x : a.w;
-      const float d0 = rot & 2 ? b2 : b0, d1 = rot & 2 ? b3 : b1, d2 = rot & 2 ? b0 : b2, d3 = rot & 2 ? b1 : b3;
-      float* row = s_out + (size_t)(4 * QL * u + 4 * q) * S + bin;     // d_j is component (j + rot) & 3
-      row[((0 + rot) & 3) * S] = d0;
-      row[((1 + rot) & 3) * S] = d1;
-      row[((2 + rot) & 3) * S] = d2;
-      row[((3 + rot) & 3) * S] = d3;
+    for (int i = 0; i < 4; i++) {
+      float* t = &tile[row][4 * ((threadIdx.x & 7) + 8 * i)];
+      t[0] = v[i].x; t[1] = v[i].y; t[2] = v[i].z; t[3] = v[i].w;
     }
   }
   __syncthreads();
+  {
+    const int cq = threadIdx.x & 7, c = c0 + 4 * cq;               // channel quad
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int px = (threadIdx.x >> 3) + 32 * i, p = p0 + px;
+      if (p < HW && c < C)
+        *reinterpret_cast<float4*>(dst + (size_t)p * C + c) =
+            make_float4(tile[4 * cq + 0][px], tile[4 * cq + 1][px], tile[4 * cq + 2][px], tile[4 * cq + 3][px]);
+    }
+  }
+}
+
+// grid = (tiles_x + tables_per_row, tiles_y * B): in every grid row the first tiles_x CTAs transpose a tile, the
+// rest build tables (tables_per_row = ceil(R / rows)), so both kinds of work are in flight throughout and no
+// index needs a division.  tiles_x == 0: tables only (channel-last input).
+template <int VERSION>
+__global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restrict__ in, float* __restrict__ nhwc, int C, int H,
+                                                            int W, int tiles_x, int tiles_y, const float* __restrict__ rois,
+                                                            unsigned R, int PH, int PW, float spatial_scale, int sample_num,
+                                                            unsigned char* __restrict__ tables, bool vec) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if ((int)blockIdx.x < tiles_x) {
+    const int b = tiles_y > 0 ? blockIdx.y / tiles_y : 0, ty = blockIdx.y - b * tiles_y;
+    if (vec) relayout_tile_v4(in, nhwc, C, H * W, b, blockIdx.x * kTileW, ty * 32, reinterpret_cast<float(*)[kTileW + 1]>(smem));
+    else relayout_tile(in, nhwc, C, H * W, b, blockIdx.x * 32, ty * 32, reinterpret_cast<float(*)[33]>(smem));
+    return;
+  }
+  const unsigned idx = blockIdx.y * (gridDim.x - tiles_x) + (blockIdx.x - tiles_x);
+  if (idx >= R) return;
+  const int nbins = PH * PW;
+  __shared__ RoiGeom g;
+  if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)idx * 6, spatial_scale, sample_num, PH, PW);
+  __syncthreads();
+  const int fstride = roi_table_fstride(sample_num);
+  int4* hdr = reinterpret_cast<int4*>(smem);                       // the record, in its final layout
+  int* cnt = reinterpret_cast<int*>(hdr + 1);
+  int2* fin = reinterpret_cast<int2*>(cnt + ((nbins + 3) & ~3));
+  int2* raw = fin + nbins * fstride;
+  if (threadIdx.x == 0) *hdr = make_int4(g.batch, __float_as_int(g.inv_count), fstride, 0);
+  build_tap_table<VERSION>(g, nbins, PW, H, W, raw, fin, fstride, cnt);
+  const size_t stride = roi_table_stride(nbins, sample_num);
+  int4* dst = reinterpret_cast<int4*>(tables + (size_t)idx * stride);
+  for (int i = threadIdx.x; i < (int)(stride / 16); i += blockDim.x) dst[i] = hdr[i];
+}
+
+// ---- gather kernel ------------------------------------------------------------------------------------
+// grid = (R, C / SLAB), SLAB = 4*QL channels.  QL lanes span a bin's channels (QL = 32: one bin per warp, every
+// tap is 512 contiguous bytes of one channel-last pixel).  The CTA copies its RoI's table record (6.7 KB at
+// 7x7x2x2) into smem and then does nothing but loads and FMAs: bins are handed to warps through an smem counter
+// (their tap counts differ).  The output slab (SLAB x PH*PW, contiguous in (R,C,PH,PW)) is assembled in smem
+// and leaves as ONE cp.async.bulk store.
+// (256, 4): without a blocks-per-SM hint ptxas squeezes the kernel into 32 registers by sinking every load next
+// to its FMAs; 64 registers keep the 8 loads of a step in flight.
+template <int QL>
+__global__ void __launch_bounds__(256, 4) roi_gather_kernel(const float* __restrict__ feat_nhwc,
+                                                             const unsigned char* __restrict__ tables, size_t stride, int C,
+                                                             int H, int W, int nbins, float* __restrict__ out) {
+  constexpr int SLAB = 4 * QL;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int r = blockIdx.x, c0 = blockIdx.y * SLAB;
+  const int S = nbins | 1;                                         // odd row stride of s_out: see the store below
+  float* s_out = reinterpret_cast<float*>(smem);                   // [SLAB][S]
+  int4* rec = reinterpret_cast<int4*>(s_out + ((SLAB * S + 3) & ~3));
+  __shared__ int next_bin;
+  {
+    const int4* src = reinterpret_cast<const int4*>(tables + (size_t)r * stride);
+    for (int i = threadIdx.x; i < (int)(stride / 16); i += blockDim.x) rec[i] = __ldg(src + i);
+    if (threadIdx.x == 0) next_bin = 0;
+  }
+  __syncthreads();
+  const int batch = rec[0].x, fstride = rec[0].z;
+  const float count = __int_as_float(rec[0].y);
+  const int* cnt = reinterpret_cast<const int*>(rec + 1);
+  const int2* fin = reinterpret_cast<const int2*>(cnt + ((nbins + 3) & ~3));
+
+  const int lane = threadIdx.x & 31, q = lane % QL;                // channel quad within a 128-channel group
+  const unsigned gmask = QL == 32 ? 0xffffffffu : (((1u << QL) - 1u) << (lane & ~(QL - 1)));
+  const float* base = feat_nhwc + (size_t)batch * H * W * C + c0 + 4 * q;
+  const int icnt = (int)count;
+  const bool pow2 = (icnt & (icnt - 1)) == 0;                      // x / 2^k == x * 2^-k exactly
+  const float rcnt = 1.f / count;
+  const int rot = (q >> 3) & 3;
+  const int ro0 = (4 * q + ((0 + rot) & 3)) * S, ro1 = (4 * q + ((1 + rot) & 3)) * S;
+  const int ro2 = (4 * q + ((2 + rot) & 3)) * S, ro3 = (4 * q + ((3 + rot) & 3)) * S;
+  for (;;) {
+    int bin = 0;
+    if (q == 0) bin = atomicAdd(&next_bin, 1);
+    bin = __shfl_sync(gmask, bin, lane & ~(QL - 1));
+    if (bin >= nbins) break;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int2* e = fin + bin * fstride;
+    const int n = cnt[bin];
+    // One latency round per 8 taps: the loads of a step are all issued before its first FMA (a load costs ~1000
+    // cycles under load; two thirds of the bins have <= 8 taps).  Full steps carry no predicates; the ragged tail
+    // is one more step of (4 plain +) up to 3 predicated loads — never dummy loads: every 512-B tap costs ~8
+    // cycles of the SM's L1 data path whether it hits or not, and that path and the issue slots, not HBM or L2,
+    // are what this kernel runs out of.
+#define JDET_TAP_ADDR(j) (base + (size_t)(unsigned)t[j].x * (unsigned)C)
+#define JDET_TAP_FMA(j)                                                                                                \
+  do {                                                                                                                 \
+    const float w_ = __int_as_float(t[j].y);                                                                           \
+    acc.x += w_ * v[j].x; acc.y += w_ * v[j].y; acc.z += w_ * v[j].z; acc.w += w_ * v[j].w;                            \
+  } while (0)
+    int k = 0;
+    for (; n - k >= 8; k += 8) {
+      int2 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const int4 two = *reinterpret_cast<const int4*>(e + k + j);
+        t[j] = make_int2(two.x, two.y);
+        t[j + 1] = make_int2(two.z, two.w);
+      }
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = __ldg(reinterpret_cast<const float4*>(JDET_TAP_ADDR(j)));
+#pragma unroll
+      for (int j = 0; j < 8; j++) JDET_TAP_FMA(j);
+    }
+    const int rem = n - k;                                           // 0..7 taps left; the table is readable (and zero-weighted) up to k + 8
+    if (rem >= 4) {
+      int2 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const int4 two = *reinterpret_cast<const int4*>(e + k + j);
+        t[j] = make_int2(two.x, two.y);
+        t[j + 1] = make_int2(two.z, two.w);
+      }
+      float4 v[7];
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = __ldg(reinterpret_cast<const float4*>(JDET_TAP_ADDR(j)));
+#pragma unroll
+      for (int j = 4; j < 7; j++) v[j] = ldg_v4_if(JDET_TAP_ADDR(j), j < rem);
+#pragma unroll
+      for (int j = 0; j < 7; j++) JDET_TAP_FMA(j);
+    } else if (rem > 0) {
+      int2 t[4];
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const int4 two = *reinterpret_cast<const int4*>(e + k + j);
+        t[j] = make_int2(two.x, two.y);
+        t[j + 1] = make_int2(two.z, two.w);
+      }
+      float4 v[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) v[j] = ldg_v4_if(JDET_TAP_ADDR(j), j < rem);
+#pragma unroll
+      for (int j = 0; j < 3; j++) JDET_TAP_FMA(j);
+    }
+#undef JDET_TAP_ADDR
+#undef JDET_TAP_FMA
+    // s_out[channel][bin], row stride S odd.  A lane's 4 channels are 4 rows apart from its neighbour's, so
+    // a plain store would hit 8 banks 4 lanes deep; lanes 8 apart instead store their components in a
+    // rotated order (rot = lane/8), which spreads every store instruction over all 32 banks.
+    {
+      float4 a = acc;
+      if (pow2) { a.x *= rcnt; a.y *= rcnt; a.z *= rcnt; a.w *= rcnt; }
+      else { a.x /= count; a.y /= count; a.z /= count; a.w /= count; }
+      const float b0 = rot & 1 ? a.y : a.x, b1 = rot & 1 ? a.z : a.y, b2 = rot & 1 ? a.w : a.z, b3 = rot & 1 ? a.x : a.w;
+      const float d0 = rot & 2 ? b2 : b0, d1 = rot & 2 ? b3 : b1, d2 = rot & 2 ? b0 : b2, d3 = rot & 2 ? b1 : b3;
+      float* row = s_out + bin;                                     // d_j is component (j + rot) & 3 of this lane's channel quad
+      row[ro0] = d0;
+      row[ro1] = d1;
+      row[ro2] = d2;
+      row[ro3] = d3;
+    }
+  }
   // out[r][c0 .. c0+SLAB-1][bins] is one contiguous run of SLAB*nbins floats
   float* dst = out + ((size_t)r * C + c0) * nbins;
   const int total = SLAB * nbins;
-  if (S == nbins && (total & 3) == 0 && ((((size_t)r * C + c0) * nbins) & 3) == 0) {
-    for (int i = threadIdx.x * 4; i < total; i += blockDim.x * 4) {
-      const float4 v = *reinterpret_cast<const float4*>(s_out + i);
-      st_stream_v4(dst + i, v.x, v.y, v.z, v.w);
+  if (S == nbins && (total & 3) == 0 && (((uintptr_t)dst) & 15) == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the bulk copy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                   "r"((uint32_t)__cvta_generic_to_shared(s_out)), "r"((uint32_t)total * 4u)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // smem may be released once it has been read
     }
   } else {
+    __syncthreads();
     for (int i = threadIdx.x; i < total; i += blockDim.x) st_stream(dst + i, s_out[(i / nbins) * S + i % nbins]);
   }
 }
@@ -354,7 +490,7 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nhwc_kernel(const float* __
   int* cnt = reinterpret_cast<int*>(s_go + SLAB * nbins);
   const float* src = grad_out + ((size_t)r * C + c0) * nbins;
   for (int i = threadIdx.x; i < SLAB * nbins; i += blockDim.x) s_go[i] = __ldg(src + i);
-  build_tap_table<VERSION>(g, nbins, PW, H, W, raw, fin, cnt);  // one atomic per distinct pixel of a bin
+  build_tap_table<VERSION>(g, nbins, PW, H, W, raw, fin, tpb, cnt);  // one atomic per distinct pixel of a bin
   float* base = grad_nhwc + (size_t)g.batch * H * W * C + c0;
   const int q = threadIdx.x % QL;
   const float cntf = (float)spb;                     // the backward divides by gh*gw in both versions
@@ -420,12 +556,56 @@ static bool use_staged(int B, int C, int H, int W, int R, int PH, int PW, int sa
   return (long long)R * PH * PW * sample_num * sample_num * 8 >= (long long)B * H * W;
 }
 
+// prologue (tables, + re-layout when `input` is NCHW) and gather from the channel-last map
+static cudaError_t launch_staged(int version, const float* input_nchw, const float* nhwc_in, float* nhwc_scratch,
+                                 unsigned char* tables, const float* rois, int B, int C, int H, int W, int R, int PH, int PW,
+                                 float spatial_scale, int sampling_ratio, float* output, cudaStream_t st) {
+  const int nbins = PH * PW;
+  const size_t stride = roi_table_stride(nbins, sampling_ratio);
+  {
+    const bool vec = input_nchw && ((H * W) & 3) == 0 && (C & 3) == 0 && ((((uintptr_t)input_nchw) | ((uintptr_t)nhwc_scratch)) & 15) == 0;
+    const int tiles_x = input_nchw ? jdet_ceil_div(H * W, vec ? kTileW : 32) : 0, tiles_y = input_nchw ? jdet_ceil_div(C, 32) : 0;
+    const int rows = input_nchw ? tiles_y * B : jdet_ceil_div(R, 1024);
+    if (rows > 65535) return cudaErrorInvalidConfiguration;
+    dim3 pgrid(tiles_x + jdet_ceil_div(R, rows), rows);
+    const size_t smem = std::max(stride + (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2), sizeof(float) * 32 * (kTileW + 1));
+    if (version == 1) {
+      if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
+      roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)R, PH, PW, spatial_scale, sampling_ratio, tables, vec);
+    } else {
+      if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
+      roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)R, PH, PW, spatial_scale, sampling_ratio, tables, vec);
+    }
+  }
+  const float* nhwc = input_nchw ? nhwc_scratch : nhwc_in;
+  const int slab = (C % 128 == 0) ? 128 : 64;
+  const size_t smem = (((size_t)slab * (nbins | 1) + 3) & ~(size_t)3) * 4 + stride;
+  dim3 grid(R, C / slab);
+  // (measured on B200, cfg2, gather only: 16 taps per bin straight from per-CTA tables 106 us; taps merged per bin
+  //  95 us; tables moved to the prologue, no other change 90 us; 8 loads per step actually in flight (see the
+  //  launch bounds) and unpredicated steps: see profiles/)
+#define JDET_LAUNCH_ROI(QL_)                                                                                           \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_gather_kernel<QL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; } \
+    roi_gather_kernel<QL_><<<grid, 256, smem, st>>>(nhwc, tables, stride, C, H, W, nbins, output);                    \
+  } while (0)
+  if (slab == 128) JDET_LAUNCH_ROI(32); else JDET_LAUNCH_ROI(16);
+#undef JDET_LAUNCH_ROI
+  return cudaGetLastError();
+}
+
 }  // namespace jdet
 
 JDET_API size_t jdet_roi_align_rotated_workspace_bytes(int B, int C, int H, int W, int R, int PH, int PW,
                                                        int sampling_ratio) {
   if (!jdet::use_staged(B, C, H, W, R, PH, PW, sampling_ratio)) return 256;
-  return jdet_align_up((size_t)B * C * H * W * sizeof(float), 256);
+  return jdet_align_up((size_t)B * C * H * W * sizeof(float), 256) +          // channel-last copy
+         jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256);   // tap tables
+}
+
+JDET_API size_t jdet_roi_align_rotated_nhwc_workspace_bytes(int R, int PH, int PW, int sampling_ratio) {
+  if (sampling_ratio <= 0 || R <= 0 || PH <= 0 || PW <= 0) return 256;
+  return jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256);
 }
 
 // version 1: ROIAlignRotated_v1 / roi_align (ops/roi_align_rotated_v1.py:300-326,355-365)
@@ -441,27 +621,12 @@ JDET_API int jdet_roi_align_rotated(int version, const float* input, int B, int 
   if (R == 0 || C == 0) return 0;
   if (!input || !rois || !output || B == 0 || H == 0 || W == 0) return JDET_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nbins = PH * PW;
   if (use_staged(B, C, H, W, R, PH, PW, sampling_ratio)) {
-    const size_t need = jdet_align_up((size_t)B * C * H * W * sizeof(float), 256);
-    if (!workspace || workspace_bytes < need) return JDET_ERR_WORKSPACE;
-    float* nhwc = (float*)workspace;
-    launch_nchw_to_nhwc(input, nhwc, B, C, H * W, st);
-    const int slab = (C % 256 == 0) ? 256 : (C % 128 == 0) ? 128 : 64;
-    const size_t slot_bytes = (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2);
-    const size_t smem = slot_bytes + (size_t)((nbins + 3) & ~3) * 4 + std::max(slot_bytes, (size_t)slab * (nbins | 1) * 4);
-    dim3 grid(R, C / slab);
-    // (measured on B200, cfg2, same relayout: (RoI, 64-ch slab) CTAs with 16 undeduplicated taps 146 us; 128-ch
-    //  slabs 136 us; tap merging by a serial per-bin pass 185-250 us, by a parallel pass without compaction 147 us)
-#define JDET_LAUNCH_ROI(V, QL_, NQ_)                                                                                   \
-  do {                                                                                                                 \
-    if (smem > 48 * 1024)                                                                                              \
-      JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(roi_align_nhwc_kernel<V, QL_, NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    roi_align_nhwc_kernel<V, QL_, NQ_><<<grid, 256, smem, st>>>(nhwc, rois, C, H, W, PH, PW, spatial_scale, sampling_ratio, output);        \
-  } while (0)
-    if (version == 1) { if (slab == 256) JDET_LAUNCH_ROI(1, 32, 2); else if (slab == 128) JDET_LAUNCH_ROI(1, 32, 1); else JDET_LAUNCH_ROI(1, 16, 1); }
-    else              { if (slab == 256) JDET_LAUNCH_ROI(0, 32, 2); else if (slab == 128) JDET_LAUNCH_ROI(0, 32, 1); else JDET_LAUNCH_ROI(0, 16, 1); }
-#undef JDET_LAUNCH_ROI
+    const size_t map_bytes = jdet_align_up((size_t)B * C * H * W * sizeof(float), 256);
+    if (!workspace || workspace_bytes < jdet_roi_align_rotated_workspace_bytes(B, C, H, W, R, PH, PW, sampling_ratio))
+      return JDET_ERR_WORKSPACE;
+    JDET_RETURN_IF_CUDA(launch_staged(version, input, nullptr, (float*)workspace, (unsigned char*)workspace + map_bytes, rois, B, C,
+                                      H, W, R, PH, PW, spatial_scale, sampling_ratio, output, st));
   } else {
     const int ch_per_cta = 32;
     const size_t smem = (size_t)kMaxSamples * sizeof(SampleTap);
@@ -474,11 +639,29 @@ JDET_API int jdet_roi_align_rotated(int version, const float* input, int B, int 
   return (int)cudaGetLastError();
 }
 
+// channel-last input: no re-layout (include/jdet_b200.h)
+JDET_API int jdet_roi_align_rotated_nhwc(int version, const float* input_nhwc, int B, int C, int H, int W, const float* rois,
+                                         int R, int PH, int PW, float spatial_scale, int sampling_ratio, float* output,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace jdet;
+  if ((version != 0 && version != 1) || B < 0 || C < 0 || H < 0 || W < 0 || R < 0 || PH <= 0 || PW <= 0)
+    return JDET_ERR_BAD_ARG;
+  if (R == 0 || C == 0) return 0;
+  if (!input_nhwc || !rois || !output || B == 0 || H == 0 || W == 0) return JDET_ERR_BAD_ARG;
+  if (sampling_ratio <= 0 || C % 64 != 0 || (long long)PH * PW * sampling_ratio * sampling_ratio > kMaxSamples)
+    return JDET_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < jdet_roi_align_rotated_nhwc_workspace_bytes(R, PH, PW, sampling_ratio))
+    return JDET_ERR_WORKSPACE;
+  return (int)launch_staged(version, nullptr, input_nhwc, nullptr, (unsigned char*)workspace, rois, B, C, H, W, R, PH, PW,
+                            spatial_scale, sampling_ratio, output, (cudaStream_t)stream);
+}
+
 // backward of jdet_roi_align_rotated w.r.t. input: _RotatedROIAlign[_v1].grad (roi_align_rotated_v1.py:328-351,
 // roi_align_rotated.py:285-308).  grad_output (R,C,PH,PW) -> grad_input (B,C,H,W), written in full.
 JDET_API size_t jdet_roi_align_rotated_backward_workspace_bytes(int B, int C, int H, int W, int R, int PH, int PW,
                                                                 int sampling_ratio) {
-  return jdet_roi_align_rotated_workspace_bytes(B, C, H, W, R, PH, PW, sampling_ratio);
+  if (!jdet::use_staged(B, C, H, W, R, PH, PW, sampling_ratio)) return 256;
+  return jdet_align_up((size_t)B * C * H * W * sizeof(float), 256);
 }
 
 JDET_API int jdet_roi_align_rotated_backward(int version, const float* grad_output, const float* rois, int R, int B, int C,

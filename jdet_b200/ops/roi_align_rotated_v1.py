@@ -16,16 +16,29 @@ def _pair(v):
 def _roi_align_impl(version, input, rois, output_size, spatial_scale, sampling_ratio):
     assert rois.shape[1] == 6                                  # roi_align_rotated_v1.py:306
     require_cuda(input, rois)
-    x, r = f32c(input), f32c(rois)
-    assert x.dim() == 4
+    assert input.dim() == 4
     ph, pw = _pair(output_size)
-    B, C, H, W = x.shape
+    B, C, H, W = input.shape
+    r = f32c(rois)
     R = r.shape[0]
-    out = torch.empty((R, C, ph, pw), dtype=torch.float32, device=x.device)
+    out = torch.empty((R, C, ph, pw), dtype=torch.float32, device=input.device)
     if out.numel() == 0:
         return out
     sr = int(sampling_ratio)        # the reference passes a float constant to an int parameter (truncation)
     L = lib()
+    # a map that is already channel-last in memory (torch.channels_last) is gathered in place: no re-layout pass
+    if (input.dtype == torch.float32 and C > 1 and not input.is_contiguous()
+            and input.is_contiguous(memory_format=torch.channels_last)):
+        with torch.cuda.device(input.device):
+            ws = scratch(L.jdet_roi_align_rotated_nhwc_workspace_bytes(R, ph, pw, sr), input.device)
+            rc = L.jdet_roi_align_rotated_nhwc(version, input.data_ptr(), B, C, H, W, r.data_ptr(), R, ph, pw,
+                                               float(spatial_scale), sr, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               stream_ptr(input.device))
+        if rc == 0:
+            return out
+        if rc != -3:                # JDET_ERR_UNSUPPORTED: shape outside the channel-last kernel -> NCHW entry point
+            check(rc, "roi_align_rotated_nhwc")
+    x = f32c(input)
     with torch.cuda.device(x.device):
         ws = scratch(L.jdet_roi_align_rotated_workspace_bytes(B, C, H, W, R, ph, pw, sr), x.device)
         check(L.jdet_roi_align_rotated(version, x.data_ptr(), B, C, H, W, r.data_ptr(), R, ph, pw,

@@ -249,6 +249,23 @@ def test_roi_align_vs_oracle(version, cfg):
         assert np.abs(got - ref).max() <= TOL, np.abs(got - ref).max()
 
 
+@pytest.mark.parametrize("version", [0, 1])
+def test_roi_align_channels_last_input(version):
+    """A torch.channels_last map takes the no-relayout entry point (jdet_roi_align_rotated_nhwc); same numbers as NCHW.
+    A shape the channel-last kernel refuses (C % 64 != 0) silently takes the NCHW entry point."""
+    rng = np.random.default_rng(31)
+    for C, sr in ((256, 2), (64, 2), (24, 2)):
+        x = rng.standard_normal((2, C, 40, 48)).astype(np.float32)
+        rois = _rois(rng, 300, 2, 160.0, 4, 96)
+        mod = ops().roi_align_rotated_v1 if version == 1 else ops().roi_align_rotated
+        xcl = cu(x).contiguous(memory_format=torch.channels_last)
+        assert not xcl.is_contiguous()
+        got = mod.roi_align(xcl, cu(rois), (7, 7), 0.25, sr).cpu().numpy()
+        want = oracle.roi_align_rotated(x, rois, (7, 7), 0.25, sr, version)
+        assert np.abs(got - want).max() <= TOL
+        assert np.array_equal(got, mod.roi_align(cu(x), cu(rois), (7, 7), 0.25, sr).cpu().numpy()) or C == 24
+
+
 def test_roi_align_module_and_reference_selftest_shape():
     """ops/roi_align_rotated_v1.py:376-386: feature (2,1024,64,64), the two literal RoIs, 7x7, 1/16."""
     rng = np.random.default_rng(2)

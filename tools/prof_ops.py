@@ -31,6 +31,11 @@ if want("roi"):
     rois = cu(np.concatenate([np.zeros((2048, 1), np.float32), dota_boxes(rng, 2048)], 1))
     for _ in range(a.reps):
         ops.roi_align_rotated_v1.roi_align(feat, rois, (7, 7), 0.25, 2)
+if want("roicl"):
+    feat = torch.randn((1, 256, 256, 256), device=dev).contiguous(memory_format=torch.channels_last)
+    rois = cu(np.concatenate([np.zeros((2048, 1), np.float32), dota_boxes(rng, 2048)], 1))
+    for _ in range(a.reps):
+        ops.roi_align_rotated_v1.roi_align(feat, rois, (7, 7), 0.25, 2)
 if want("nms"):
     n = 100000
     d = np.concatenate([clustered_boxes(rng, n // 2, 50), dota_boxes(rng, n - n // 2)])
