@@ -187,14 +187,17 @@ def run_ours(args):
     value = n_rois * world / (ms_per_step * 1e-3)
     alg_bytes = feat.numel() * 4 + rois.numel() * 4 + out.numel() * 4        # 169 918 464 B
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "roi_align_rotated = nchw_to_nhwc_kernel + roi_align_nhwc_kernel<1,128> (2 launches per step)",
+    roofline = {"bound": "hbm",
+                "kernel": "roi_align_rotated = roi_prologue_kernel<1> (re-layout + tap tables) + roi_gather_kernel<32> "
+                          "(2 launches per step; the duration used is the WHOLE step, dominant kernel = the gather, ~69 % of it)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "peak_source": peaks["source"], "algorithmic_bytes": alg_bytes,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels from the committed ncu --set full
-                # capture (profiles/r01_ncu_summary.md): relayout 67.1 + 26.0 MB, gather 68.0 + 54.3 MB
-                "traffic": 215_400_000,
-                "note": "the gather is bound by the L1 data path (l1tex 77 %): 16 taps x 16 B per (bin, channel quad) = "
-                        "1.43 GB through L1 per launch; HBM traffic is at the algorithmic minimum"}
+                # capture (profiles/r01_ncu_summary.md, cold L2): prologue 67.2 + 31.8 MB, gather 134.2 + 73.4 MB
+                "traffic": 306_600_000,
+                "note": "the gather is bound by the SM's L1 data path and issue slots (l1tex 57 %, issue 60 %, no DRAM/L2 "
+                        "limit in sight: an L2-resident random 1-KB gather probe reaches 19-20 TB/s on this GPU, "
+                        "profiles/r01_l2_gather_probe.txt); 0.80 GB of taps cross L1 per launch after per-bin merging"}
 
     # ---- e2e: host buffers, H2D + op + D2H inside the timed region ----------------------------
     # Three streams (H2D / op / D2H), two buffers: step i+1's upload overlaps step i's op and download

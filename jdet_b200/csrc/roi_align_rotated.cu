@@ -246,8 +246,10 @@ template <int VERSION>
 __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restrict__ in, float* __restrict__ nhwc, int C, int H,
                                                             int W, int tiles_x, int tiles_y, const float* __restrict__ rois,
                                                             unsigned R, int PH, int PW, float spatial_scale, int sample_num,
-                                                            unsigned char* __restrict__ tables, bool vec) {
+                                                            unsigned char* __restrict__ tables, bool vec,
+                                                            int* __restrict__ work_counter) {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *work_counter = 0;   // the gather's work queue (next launch on the stream)
   if ((int)blockIdx.x < tiles_x) {
     const int b = tiles_y > 0 ? blockIdx.y / tiles_y : 0, ty = blockIdx.y - b * tiles_y;
     if (vec) relayout_tile_v4(in, nhwc, C, H * W, b, blockIdx.x * kTileW, ty * 32, reinterpret_cast<float(*)[kTileW + 1]>(smem));
@@ -283,34 +285,62 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
 template <int QL>
 __global__ void __launch_bounds__(256, 4) roi_gather_kernel(const float* __restrict__ feat_nhwc,
                                                              const unsigned char* __restrict__ tables, size_t stride, int C,
-                                                             int H, int W, int nbins, float* __restrict__ out) {
+                                                             int H, int W, int nbins, int nslabs, int items,
+                                                             int* __restrict__ work_counter, float* __restrict__ out) {
   constexpr int SLAB = 4 * QL;
   extern __shared__ __align__(128) unsigned char smem[];
-  const int r = blockIdx.x, c0 = blockIdx.y * SLAB;
   const int S = nbins | 1;                                         // odd row stride of s_out: see the store below
   float* s_out = reinterpret_cast<float*>(smem);                   // [SLAB][S]
-  int4* rec = reinterpret_cast<int4*>(s_out + ((SLAB * S + 3) & ~3));
-  __shared__ int next_bin;
-  {
-    const int4* src = reinterpret_cast<const int4*>(tables + (size_t)r * stride);
-    for (int i = threadIdx.x; i < (int)(stride / 16); i += blockDim.x) rec[i] = __ldg(src + i);
-    if (threadIdx.x == 0) next_bin = 0;
-  }
-  __syncthreads();
-  const int batch = rec[0].x, fstride = rec[0].z;
-  const float count = __int_as_float(rec[0].y);
-  const int* cnt = reinterpret_cast<const int*>(rec + 1);
-  const int2* fin = reinterpret_cast<const int2*>(cnt + ((nbins + 3) & ~3));
-
+  unsigned char* rec_base = reinterpret_cast<unsigned char*>(s_out + ((SLAB * S + 3) & ~3));   // 2 table records
+  __shared__ uint64_t full[2];
+  __shared__ int next_bin, s_next_item;
   const int lane = threadIdx.x & 31, q = lane % QL;                // channel quad within a 128-channel group
   const unsigned gmask = QL == 32 ? 0xffffffffu : (((1u << QL) - 1u) << (lane & ~(QL - 1)));
-  const float* base = feat_nhwc + (size_t)batch * H * W * C + c0 + 4 * q;
-  const int icnt = (int)count;
-  const bool pow2 = (icnt & (icnt - 1)) == 0;                      // x / 2^k == x * 2^-k exactly
-  const float rcnt = 1.f / count;
   const int rot = (q >> 3) & 3;
   const int ro0 = (4 * q + ((0 + rot) & 3)) * S, ro1 = (4 * q + ((1 + rot) & 3)) * S;
   const int ro2 = (4 * q + ((2 + rot) & 3)) * S, ro3 = (4 * q + ((3 + rot) & 3)) * S;
+
+  // Persistent CTA: work items (RoI, slab) come from a global counter (RoIs differ 4x in taps); the table of the
+  // NEXT item is fetched by a bulk-async copy while the current one is gathered, and the slab store of the
+  // PREVIOUS item drains while the current one runs — a CTA never sits waiting for its 6.7 KB table or its store.
+  int cur = blockIdx.x;                                            // first item: static; later ones from the counter
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init_fence();
+    if (cur < items) {
+      mbar_expect_tx(&full[0], (uint32_t)stride);
+      bulk_g2s(rec_base, tables + (size_t)(cur / nslabs) * stride, (uint32_t)stride, &full[0]);
+    }
+  }
+  __syncthreads();
+  uint32_t buf = 0, phases = 0;                                    // bit b: parity to wait for on full[b]
+  while (cur < items) {
+    if (threadIdx.x == 0) {
+      next_bin = 0;
+      bulk_s2g_wait_read();                                        // the previous slab has left s_out
+    }
+    mbar_wait(&full[buf], (phases >> buf) & 1u);                   // this item's table has landed
+    phases ^= 1u << buf;
+    __syncthreads();
+    if (threadIdx.x == 0) {                                        // after the barrier: nobody waits on the atomic's round trip
+      const int nx = atomicAdd(work_counter, 1) + (int)gridDim.x;
+      s_next_item = nx;                                            // read by everyone after the barrier before the store
+      if (nx < items) {
+        mbar_expect_tx(&full[buf ^ 1], (uint32_t)stride);
+        bulk_g2s(rec_base + (buf ^ 1) * stride, tables + (size_t)(nx / nslabs) * stride, (uint32_t)stride, &full[buf ^ 1]);
+      }
+    }
+    const int r = cur / nslabs, c0 = (cur - r * nslabs) * SLAB;
+    const int4* rec = reinterpret_cast<const int4*>(rec_base + buf * stride);
+    const int batch = rec[0].x, fstride = rec[0].z;
+    const float count = __int_as_float(rec[0].y);
+    const int* cnt = reinterpret_cast<const int*>(rec + 1);
+    const int2* fin = reinterpret_cast<const int2*>(cnt + ((nbins + 3) & ~3));
+    const float* base = feat_nhwc + (size_t)batch * H * W * C + c0 + 4 * q;
+    const int icnt = (int)count;
+    const bool pow2 = (icnt & (icnt - 1)) == 0;                    // x / 2^k == x * 2^-k exactly
+    const float rcnt = 1.f / count;
   for (;;) {
     int bin = 0;
     if (q == 0) bin = atomicAdd(&next_bin, 1);
@@ -393,23 +423,21 @@ __global__ void __launch_bounds__(256, 4) roi_gather_kernel(const float* __restr
       row[ro3] = d3;
     }
   }
-  // out[r][c0 .. c0+SLAB-1][bins] is one contiguous run of SLAB*nbins floats
-  float* dst = out + ((size_t)r * C + c0) * nbins;
-  const int total = SLAB * nbins;
-  if (S == nbins && (total & 3) == 0 && (((uintptr_t)dst) & 15) == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the bulk copy
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                   "r"((uint32_t)__cvta_generic_to_shared(s_out)), "r"((uint32_t)total * 4u)
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // smem may be released once it has been read
+    // out[r][c0 .. c0+SLAB-1][bins] is one contiguous run of SLAB*nbins floats
+    float* dst = out + ((size_t)r * C + c0) * nbins;
+    const int total = SLAB * nbins;
+    if (S == nbins && (total & 3) == 0 && (((uintptr_t)dst) & 15) == 0) {
+      fence_proxy_async_smem();                                    // generic-proxy smem writes -> visible to the bulk copy
+      __syncthreads();
+      if (threadIdx.x == 0) bulk_s2g(dst, s_out, (uint32_t)total * 4u);
+    } else {
+      __syncthreads();
+      for (int i = threadIdx.x; i < total; i += blockDim.x) st_stream(dst + i, s_out[(i / nbins) * S + i % nbins]);
     }
-  } else {
-    __syncthreads();
-    for (int i = threadIdx.x; i < total; i += blockDim.x) st_stream(dst + i, s_out[(i / nbins) * S + i % nbins]);
+    cur = s_next_item;                                             // (rewritten only after the next item's first barrier)
+    buf ^= 1u;
   }
+  if (threadIdx.x == 0) bulk_s2g_wait_read();                      // smem must outlive the last store's read
 }
 
 // ---- direct NCHW kernel --------------------------------------------------------------------------
@@ -562,6 +590,7 @@ static cudaError_t launch_staged(int version, const float* input_nchw, const flo
                                  float spatial_scale, int sampling_ratio, float* output, cudaStream_t st) {
   const int nbins = PH * PW;
   const size_t stride = roi_table_stride(nbins, sampling_ratio);
+  int* work_counter = reinterpret_cast<int*>(tables + jdet_align_up((size_t)R * stride, 256));
   {
     const bool vec = input_nchw && ((H * W) & 3) == 0 && (C & 3) == 0 && ((((uintptr_t)input_nchw) | ((uintptr_t)nhwc_scratch)) & 15) == 0;
     const int tiles_x = input_nchw ? jdet_ceil_div(H * W, vec ? kTileW : 32) : 0, tiles_y = input_nchw ? jdet_ceil_div(C, 32) : 0;
@@ -571,23 +600,29 @@ static cudaError_t launch_staged(int version, const float* input_nchw, const flo
     const size_t smem = std::max(stride + (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2), sizeof(float) * 32 * (kTileW + 1));
     if (version == 1) {
       if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-      roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)R, PH, PW, spatial_scale, sampling_ratio, tables, vec);
+      roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)R, PH, PW, spatial_scale, sampling_ratio, tables, vec, work_counter);
     } else {
       if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-      roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)R, PH, PW, spatial_scale, sampling_ratio, tables, vec);
+      roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)R, PH, PW, spatial_scale, sampling_ratio, tables, vec, work_counter);
     }
   }
   const float* nhwc = input_nchw ? nhwc_scratch : nhwc_in;
   const int slab = (C % 128 == 0) ? 128 : 64;
-  const size_t smem = (((size_t)slab * (nbins | 1) + 3) & ~(size_t)3) * 4 + stride;
-  dim3 grid(R, C / slab);
+  const size_t smem = (((size_t)slab * (nbins | 1) + 3) & ~(size_t)3) * 4 + 2 * stride;
+  const int nslabs = C / slab;
+  const long long items_ll = (long long)R * nslabs;
+  if (items_ll > 0x7fffffffLL - 148 * 8) return cudaErrorInvalidConfiguration;
+  const int items = (int)items_ll;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = (int)std::min<long long>(items_ll, (long long)sms * 4);
   // (measured on B200, cfg2, gather only: 16 taps per bin straight from per-CTA tables 106 us; taps merged per bin
   //  95 us; tables moved to the prologue, no other change 90 us; 8 loads per step actually in flight (see the
-  //  launch bounds) and unpredicated steps: see profiles/)
+  //  launch bounds) and lean steps 71 us; persistent CTAs with table prefetch: see profiles/)
 #define JDET_LAUNCH_ROI(QL_)                                                                                           \
   do {                                                                                                                 \
     if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_gather_kernel<QL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; } \
-    roi_gather_kernel<QL_><<<grid, 256, smem, st>>>(nhwc, tables, stride, C, H, W, nbins, output);                    \
+    roi_gather_kernel<QL_><<<grid, 256, smem, st>>>(nhwc, tables, stride, C, H, W, nbins, nslabs, items, work_counter, output); \
   } while (0)
   if (slab == 128) JDET_LAUNCH_ROI(32); else JDET_LAUNCH_ROI(16);
 #undef JDET_LAUNCH_ROI
@@ -600,12 +635,12 @@ JDET_API size_t jdet_roi_align_rotated_workspace_bytes(int B, int C, int H, int 
                                                        int sampling_ratio) {
   if (!jdet::use_staged(B, C, H, W, R, PH, PW, sampling_ratio)) return 256;
   return jdet_align_up((size_t)B * C * H * W * sizeof(float), 256) +          // channel-last copy
-         jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256);   // tap tables
+         jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256) + 256;   // tap tables + work counter
 }
 
 JDET_API size_t jdet_roi_align_rotated_nhwc_workspace_bytes(int R, int PH, int PW, int sampling_ratio) {
   if (sampling_ratio <= 0 || R <= 0 || PH <= 0 || PW <= 0) return 256;
-  return jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256);
+  return jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256) + 256;
 }
 
 // version 1: ROIAlignRotated_v1 / roi_align (ops/roi_align_rotated_v1.py:300-326,355-365)
