@@ -360,6 +360,32 @@ def run_extra(torch, dist, ops, jdist, dev, rank, world, peaks, flush):
                      "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg}}
     del fcl
 
+    # cfg5 (per GPU share): Oriented R-CNN RoI stage, 2 x 1024^2 tiles, 2000 proposals each through the 4-level
+    # OrientedSingleRoIExtractor (rotated RoIAlign v1 on strides 4..32) + the shared FCs of OrientedHead
+    from jdet_b200.models.roi_heads import OrientedHead
+    gh = torch.Generator(device=dev).manual_seed(9 + rank)
+    fpn = [torch.randn((2, 256, 1024 // s, 1024 // s), device=dev, generator=gh) for s in (4, 8, 16, 32)]
+    ohead = OrientedHead(num_classes=15).to(dev).eval().requires_grad_(False)
+    props = [torch.as_tensor(np.concatenate([dota_boxes(rng, 2000, 1024.0), rng.random((2000, 1), dtype=np.float32)], 1)).to(dev)
+             for _ in range(2)]
+    rois_o = ohead.arb2roi(props)
+    ext = lambda: ohead.bbox_roi_extractor(fpn, rois_o)
+    ext()
+    K = 20
+    ms_ext = agg(time_steps(torch, ext, K, 3, flush)) / K
+    full = lambda: ohead(fpn, props)
+    full()
+    ms_full = agg(time_steps(torch, full, K, 3, flush)) / K
+    alg = sum(f.numel() for f in fpn) * 4 + rois_o.numel() * 4 + 4000 * 256 * 49 * 4
+    ex["oriented_rcnn_roi_stage"] = {
+        "metric": "RoIs/s", "value": 4000 * world / (ms_ext * 1e-3), "unit": "RoIs/s", "ms_per_step": ms_ext, "steps": K,
+        "config": {"workload": "OrientedSingleRoIExtractor: 2 images x 2000 proposals, 4 FPN levels (256 ch, strides 4-32 of 1024^2 tiles), "
+                               "ROIAlignRotated_v1 7x7 sampling 2; head_ms = extractor + 2 shared FCs + cls/reg + decode + threshold",
+                   "head_ms_per_step": ms_full, "images_per_s_head": 2 * world / (ms_full * 1e-3)},
+        "roofline": {"bound": "hbm", "achieved": alg / (ms_ext * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": alg / (ms_ext * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": alg}}
+    del fpn, ohead
+
     # cfg4: S2ANet-R50-FPN shapes, bs 8: feature_refine + AlignConv over the 5 levels
     levels = [(128, 8), (64, 16), (32, 32), (16, 64), (8, 128)]
     g = torch.Generator(device=dev).manual_seed(77 + rank)

@@ -157,3 +157,60 @@ def test_s2anet_head_wiring_cpu(monkeypatch):
     fam, refine, cls, reg = head.forward_single(torch.randn(2, 256, 16, 16), 8)
     assert fam.shape == (2, 5, 16, 16) and refine.shape == (2, 16, 16, 5)
     assert cls.shape == (2, 15, 16, 16) and reg.shape == (2, 5, 16, 16)
+
+
+def test_oriented_rcnn_coders_cpu():
+    """Decoders of the Oriented R-CNN inference path (coder.py:377-438, 486-519): exact inverses on constructed cases."""
+    import math
+    import torch
+    from jdet_b200.models.boxes import (midpoint_offset_decode, oriented_delta_xywht_decode, obb2hbb, obb2poly, rectpoly2obb,
+                                        regular_obb)
+    g = torch.Generator().manual_seed(0)
+    n = 200
+    obb = torch.stack([torch.rand(n, generator=g) * 500, torch.rand(n, generator=g) * 500,
+                       40 + torch.rand(n, generator=g) * 100, 5 + torch.rand(n, generator=g) * 30,
+                       (torch.rand(n, generator=g) - 0.5) * 3.0], 1)
+    obb = regular_obb(obb)
+    poly = obb2poly(obb).reshape(n, 4, 2)
+    assert torch.allclose(rectpoly2obb(poly.reshape(n, 8)), obb, atol=1e-3)
+    # midpoint offsets of a true rectangle w.r.t. its own bounding box decode back to the rectangle
+    hbb = obb2hbb(obb)
+    assert torch.allclose(hbb[:, :2], poly.min(1)[0], atol=1e-3) and torch.allclose(hbb[:, 2:], poly.max(1)[0], atol=1e-3)
+    gx, gy = (hbb[:, 0] + hbb[:, 2]) / 2, (hbb[:, 1] + hbb[:, 3]) / 2
+    gw, gh = hbb[:, 2] - hbb[:, 0], hbb[:, 3] - hbb[:, 1]
+    top = poly[torch.arange(n), poly[..., 1].argmin(1)]          # vertex on the top edge
+    right = poly[torch.arange(n), poly[..., 0].argmax(1)]        # vertex on the right edge
+    deltas = torch.zeros(n, 6)
+    deltas[:, 4] = (top[:, 0] - gx) / gw / 0.5
+    deltas[:, 5] = (right[:, 1] - gy) / gh / 0.5
+    got = midpoint_offset_decode(hbb, deltas)
+    assert torch.allclose(got[:, :4], obb[:, :4], atol=2e-2)
+    dth = torch.remainder(got[:, 4] - obb[:, 4] + math.pi / 2, math.pi) - math.pi / 2
+    assert dth.abs().max() < 1e-3
+    # OrientedDeltaXYWHT: deltas built with the encoder's formulas decode to the target
+    roi = obb
+    tgt = regular_obb(obb + torch.tensor([3., -2., 5., 1., 0.1]))
+    c, s = torch.cos(-roi[:, 4]), torch.sin(-roi[:, 4])
+    dx = (c * (tgt[:, 0] - roi[:, 0]) + s * (tgt[:, 1] - roi[:, 1])) / roi[:, 2]
+    dy = (-s * (tgt[:, 0] - roi[:, 0]) + c * (tgt[:, 1] - roi[:, 1])) / roi[:, 3]
+    d = torch.stack([dx, dy, torch.log(tgt[:, 2] / roi[:, 2]), torch.log(tgt[:, 3] / roi[:, 3]), tgt[:, 4] - roi[:, 4]], 1)
+    stds = torch.tensor([.1, .1, .2, .2, .1])
+    back = oriented_delta_xywht_decode(roi, d / stds)
+    assert torch.allclose(back[:, :4], tgt[:, :4], atol=1e-2)
+    dth = torch.remainder(back[:, 4] - tgt[:, 4] + math.pi / 2, math.pi) - math.pi / 2
+    assert dth.abs().max() < 1e-4
+
+
+def test_horizontal_anchor_generator_cpu():
+    """anchor_generator.py:186-420: ratios x scales boxes per cell, anchor index fastest, cells row-major."""
+    import torch
+    from jdet_b200.models.boxes import AnchorGenerator
+    gen = AnchorGenerator(strides=[4, 8], ratios=[0.5, 1.0, 2.0], scales=[8])
+    a0, a1 = gen.grid_anchors([(3, 5), (2, 2)])
+    assert a0.shape == (3 * 5 * 3, 4) and a1.shape == (2 * 2 * 3, 4) and gen.num_base_anchors == [3, 3]
+    w, h = a0[:, 2] - a0[:, 0], a0[:, 3] - a0[:, 1]
+    assert torch.allclose(w * h, torch.full_like(w, 32.0 * 32.0), rtol=1e-5)            # area (stride*scale)^2 at every ratio
+    assert torch.allclose((h / w)[:3], torch.tensor([0.5, 1.0, 2.0]), rtol=1e-5)
+    ctr = (a0[:, :2] + a0[:, 2:]) / 2
+    assert torch.allclose(ctr[3:6], torch.tensor([[4.0, 0.0]]).expand(3, 2))            # second cell of the first row
+    assert torch.allclose(ctr[15:18], torch.tensor([[0.0, 4.0]]).expand(3, 2))          # first cell of the second row

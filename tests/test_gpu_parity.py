@@ -563,3 +563,37 @@ def test_s2anet_head_forward_against_oracle_ops():
         assert polys.shape == (wd.shape[0], 8) and wd.shape[0] > 0
         assert np.array_equal(lab.cpu().numpy(), wl) and np.allclose(sc.cpu().numpy(), wd[:, 5])
         assert np.allclose(polys.cpu().numpy(), rotated_box_to_poly(torch.from_numpy(wd[:, :5])).numpy(), atol=1e-3)
+
+
+@pytest.mark.gpu
+def test_oriented_rcnn_heads_forward():
+    """forward-only OrientedRPNHead -> OrientedHead on synthetic FPN maps.  The RoI features the head
+    consumes are the rotated RoIAlign kernels' output on the RPN's own proposals: checked against the oracle per level."""
+    from jdet_b200.models.roi_heads import OrientedHead, OrientedRPNHead
+    torch.manual_seed(5)
+    strides = [4, 8, 16, 32, 64]
+    feats = [torch.randn(2, 256, 256 // s, 256 // s, device="cuda") for s in strides]
+    rpn = OrientedRPNHead(256, nms_pre=500, nms_post=300).cuda().eval()
+    for m in (rpn.rpn_cls, rpn.rpn_reg):
+        torch.nn.init.normal_(m.weight, 0, 0.05)
+    props = rpn(feats)
+    assert len(props) == 2 and all(p.shape[1] == 6 and 0 < p.shape[0] <= 300 for p in props)
+    assert all(torch.isfinite(p).all() and (p[:, 2] >= p[:, 3]).all() for p in props)        # regular obb: long side first
+    assert all((p[1:, 5] <= p[:-1, 5]).all() for p in props)                                   # NMS keeps score order
+    head = OrientedHead(num_classes=15, score_thresh=0.01).cuda().eval()
+    res = head(feats, props)
+    assert len(res) == 2
+    for polys, scores, labels in res:
+        assert polys.shape[1] == 8 and polys.shape[0] == scores.shape[0] == labels.shape[0] and polys.shape[0] > 0
+        assert (scores > 0.01).all() and int(labels.max()) < 15
+    # the extractor inside the head == oracle RoIAlign v1 on the level the reference formula picks (oriented_single_level.py:91-114)
+    rois = head.arb2roi(props)
+    got = head.bbox_roi_extractor(feats[:4], rois).cpu().numpy()
+    r = rois.cpu().numpy().copy()
+    r[:, 3] *= 1.4; r[:, 4] *= 1.2
+    lvl = np.clip(np.floor(np.log2(np.sqrt(r[:, 3] * r[:, 4]) / 56 + 1e-6)), 0, 3).astype(int)
+    for l in range(4):
+        sel = np.nonzero(lvl == l)[0][:40]
+        if sel.size:
+            want = oracle.roi_align_rotated(feats[l].cpu().numpy(), r[sel], (7, 7), 1.0 / strides[l], 2, 1)
+            assert np.abs(got[sel] - want).max() <= TOL
