@@ -590,7 +590,7 @@ def test_oriented_rcnn_heads_forward():
     rois = head.arb2roi(props)
     got = head.bbox_roi_extractor(feats[:4], rois).cpu().numpy()
     r = rois.cpu().numpy().copy()
-    r[:, 3] *= 1.4; r[:, 4] *= 1.2
+    r[:, 3] *= 1.2; r[:, 4] *= 1.4                                   # extend_factor = (h, w) = (1.4, 1.2)
     lvl = np.clip(np.floor(np.log2(np.sqrt(r[:, 3] * r[:, 4]) / 56 + 1e-6)), 0, 3).astype(int)
     for l in range(4):
         sel = np.nonzero(lvl == l)[0][:40]
