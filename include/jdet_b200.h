@@ -73,6 +73,21 @@ int jdet_roi_align_rotated_nhwc(int version, const float* input_nhwc, int B, int
                                 int R, int PH, int PW, float spatial_scale, int sampling_ratio, float* output,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* the whole single-level-per-RoI FPN extractor in one call
+ * replaces: OrientedSingleRoIExtractor.execute models/roi_extractors/oriented_single_level.py:91-114 (map_roi_levels
+ *           :67-70, roi_rescale :72-88) and RboxSingleRoIExtractor.execute (rbox_single_level.py), i.e. per level a
+ *           boolean mask, a gather, the RoIAlign op and a masked "+=" into a zero-filled output.
+ * feats: HOST array of nlevels device pointers, each (B,C,Hs[l],Ws[l]) fp32 NCHW; Hs/Ws/scales: HOST arrays.
+ * A RoI (R,6) is stretched by (ext_w, ext_h), mapped to level clamp(floor(log2(sqrt(w*h)/finest_scale + 1e-6)), 0,
+ * nlevels-1), stretched by (rs_w, rs_h) and pooled at scales[level]; output (R,C,PH,PW) rows in RoI order.
+ * Needs C % 64 == 0, sampling_ratio > 0, PH*PW*sampling_ratio^2 <= 1024, nlevels <= 8 (else JDET_ERR_UNSUPPORTED). */
+size_t jdet_roi_align_rotated_fpn_workspace_bytes(int nlevels, int B, int C, const int* Hs, const int* Ws, int R, int PH,
+                                                  int PW, int sampling_ratio);
+int jdet_roi_align_rotated_fpn(int version, const float* const* feats, int nlevels, int B, int C, const int* Hs,
+                               const int* Ws, const float* scales, const float* rois, int R, int PH, int PW,
+                               int sampling_ratio, float ext_w, float ext_h, float rs_w, float rs_h, float finest_scale,
+                               float* output, void* workspace, size_t workspace_bytes, void* stream);
+
 /* backward w.r.t. input — replaces: _RotatedROIAlign[_v1].grad ops/roi_align_rotated_v1.py:328-351 (kernel :192-298),
  * ops/roi_align_rotated.py:285-308 (kernel :164-255).  grad_output (R,C,PH,PW) -> grad_input (B,C,H,W), fully written. */
 size_t jdet_roi_align_rotated_backward_workspace_bytes(int B, int C, int H, int W, int R, int PH, int PW,

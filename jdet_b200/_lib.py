@@ -32,6 +32,8 @@ SIGNATURES = {
     "jdet_roi_align_rotated": (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _i, _i, _f, _i, _p, _p, _sz, _p]),
     "jdet_roi_align_rotated_nhwc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "jdet_roi_align_rotated_nhwc": (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _i, _i, _f, _i, _p, _p, _sz, _p]),
+    "jdet_roi_align_rotated_fpn_workspace_bytes": (_sz, [_i, _i, _i, _p, _p, _i, _i, _i, _i]),
+    "jdet_roi_align_rotated_fpn": (_i, [_i, _p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _f, _f, _f, _p, _p, _sz, _p]),
     "jdet_roi_align_rotated_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "jdet_roi_align_rotated_backward": (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _sz, _p]),
     "jdet_feature_refine": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p, _p]),

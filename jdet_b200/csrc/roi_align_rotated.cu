@@ -175,9 +175,17 @@ __device__ __forceinline__ void build_tap_table(const RoiGeom& g, int nbins, int
   __syncthreads();
 }
 
+// FPN levels of one call, passed by value to the kernels.  n == 1: the plain single-map op.  n > 1: the fused
+// single-level-per-RoI extractor (OrientedSingleRoIExtractor / RboxSingleRoIExtractor.execute): a RoI is stretched
+// by (ext_w, ext_h), assigned to level clamp(floor(log2(sqrt(w*h) / finest + 1e-6)), 0, n-1), stretched again by
+// (rs_w, rs_h) and pooled from that level with the level's spatial scale.
+constexpr int kMaxLevels = 8;
+struct RoiLevel { const float* nhwc; int H, W; float scale; };
+struct RoiLevels { RoiLevel lv[kMaxLevels]; int n; float ext_w, ext_h, rs_w, rs_h, finest; };
+
 // ---- prologue kernel: per-RoI tap tables (+ the NCHW -> channel-last re-layout) -------------------------
 // Table record of one RoI in the caller's workspace (16-B granular):
-//   int4 {batch, float bits of the divisor, fin entries per bin, 0} | int cnt[nbins rounded up to 4] | int2 fin[nbins][fstride]
+//   int4 {batch, float bits of the divisor, fin entries per bin, FPN level} | int cnt[nbins rounded up to 4] | int2 fin[nbins][fstride]
 // Building it is latency-bound ALU work (double sincos, two barriers, match.any); the re-layout is an HBM
 // stream.  One launch does both, interleaved (see the kernel), so the gather CTAs start with nothing but loads
 // to do.
@@ -245,9 +253,9 @@ __device__ __forceinline__ void relayout_tile_v4(const float* __restrict__ in, f
 template <int VERSION>
 __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restrict__ in, float* __restrict__ nhwc, int C, int H,
                                                             int W, int tiles_x, int tiles_y, const float* __restrict__ rois,
-                                                            unsigned R, int PH, int PW, float spatial_scale, int sample_num,
+                                                            unsigned R, int PH, int PW, int sample_num,
                                                             unsigned char* __restrict__ tables, bool vec,
-                                                            int* __restrict__ work_counter) {
+                                                            int* __restrict__ work_counter, const __grid_constant__ RoiLevels L) {
   extern __shared__ __align__(16) unsigned char smem[];
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *work_counter = 0;   // the gather's work queue (next launch on the stream)
   if ((int)blockIdx.x < tiles_x) {
@@ -260,15 +268,33 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
   if (idx >= R) return;
   const int nbins = PH * PW;
   __shared__ RoiGeom g;
-  if (threadIdx.x == 0) g = roi_geom<VERSION>(rois + (size_t)idx * 6, spatial_scale, sample_num, PH, PW);
+  __shared__ int s_level;
+  if (threadIdx.x == 0) {
+    float roi[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) roi[i] = rois[(size_t)idx * 6 + i];
+    int level = 0;
+    if (L.n > 1) {   // map_roi_levels (oriented_single_level.py:67-70, 100-102), same fp32 operations as the torch mirror
+      roi[3] = __fmul_rn(roi[3], L.ext_w);
+      roi[4] = __fmul_rn(roi[4], L.ext_h);
+      const float side = sqrtf(__fmul_rn(roi[3], roi[4]));
+      const float lf = floorf(log2f(__fadd_rn(__fdiv_rn(side, L.finest), 1e-6f)));
+      level = lf <= 0.f ? 0 : (lf >= (float)(L.n - 1) ? L.n - 1 : (int)lf);   // NaN -> 0
+      roi[3] = __fmul_rn(roi[3], L.rs_w);
+      roi[4] = __fmul_rn(roi[4], L.rs_h);
+    }
+    s_level = level;
+    g = roi_geom<VERSION>(roi, L.lv[level].scale, sample_num, PH, PW);
+  }
   __syncthreads();
+  const int level = s_level;
   const int fstride = roi_table_fstride(sample_num);
   int4* hdr = reinterpret_cast<int4*>(smem);                       // the record, in its final layout
   int* cnt = reinterpret_cast<int*>(hdr + 1);
   int2* fin = reinterpret_cast<int2*>(cnt + ((nbins + 3) & ~3));
   int2* raw = fin + nbins * fstride;
-  if (threadIdx.x == 0) *hdr = make_int4(g.batch, __float_as_int(g.inv_count), fstride, 0);
-  build_tap_table<VERSION>(g, nbins, PW, H, W, raw, fin, fstride, cnt);
+  if (threadIdx.x == 0) *hdr = make_int4(g.batch, __float_as_int(g.inv_count), fstride, level);
+  build_tap_table<VERSION>(g, nbins, PW, L.lv[level].H, L.lv[level].W, raw, fin, fstride, cnt);
   const size_t stride = roi_table_stride(nbins, sample_num);
   int4* dst = reinterpret_cast<int4*>(tables + (size_t)idx * stride);
   for (int i = threadIdx.x; i < (int)(stride / 16); i += blockDim.x) dst[i] = hdr[i];
@@ -283,9 +309,9 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
 // (256, 4): without a blocks-per-SM hint ptxas squeezes the kernel into 32 registers by sinking every load next
 // to its FMAs; 64 registers keep the 8 loads of a step in flight.
 template <int QL>
-__global__ void __launch_bounds__(256, 4) roi_gather_kernel(const float* __restrict__ feat_nhwc,
+__global__ void __launch_bounds__(256, 4) roi_gather_kernel(const __grid_constant__ RoiLevels L,
                                                              const unsigned char* __restrict__ tables, size_t stride, int C,
-                                                             int H, int W, int nbins, int nslabs, int items,
+                                                             int nbins, int nslabs, int items,
                                                              int* __restrict__ work_counter, float* __restrict__ out) {
   constexpr int SLAB = 4 * QL;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -337,7 +363,8 @@ __global__ void __launch_bounds__(256, 4) roi_gather_kernel(const float* __restr
     const float count = __int_as_float(rec[0].y);
     const int* cnt = reinterpret_cast<const int*>(rec + 1);
     const int2* fin = reinterpret_cast<const int2*>(cnt + ((nbins + 3) & ~3));
-    const float* base = feat_nhwc + (size_t)batch * H * W * C + c0 + 4 * q;
+    const RoiLevel& lv = L.lv[rec[0].w];
+    const float* base = lv.nhwc + (size_t)batch * lv.H * lv.W * C + c0 + 4 * q;
     const int icnt = (int)count;
     const bool pow2 = (icnt & (icnt - 1)) == 0;                    // x / 2^k == x * 2^-k exactly
     const float rcnt = 1.f / count;
@@ -584,29 +611,34 @@ static bool use_staged(int B, int C, int H, int W, int R, int PH, int PW, int sa
   return (long long)R * PH * PW * sample_num * sample_num * 8 >= (long long)B * H * W;
 }
 
-// prologue (tables, + re-layout when `input` is NCHW) and gather from the channel-last map
-static cudaError_t launch_staged(int version, const float* input_nchw, const float* nhwc_in, float* nhwc_scratch,
-                                 unsigned char* tables, const float* rois, int B, int C, int H, int W, int R, int PH, int PW,
-                                 float spatial_scale, int sampling_ratio, float* output, cudaStream_t st) {
+// one prologue launch: re-layout of ONE NCHW map (input_nchw may be null) and, if with_tables, the tap tables of all RoIs
+static cudaError_t launch_prologue(int version, const float* input_nchw, float* nhwc_scratch, int B, int C, int H, int W,
+                                   bool with_tables, unsigned char* tables, int* work_counter, const float* rois, int R, int PH,
+                                   int PW, int sampling_ratio, const RoiLevels& L, cudaStream_t st) {
   const int nbins = PH * PW;
   const size_t stride = roi_table_stride(nbins, sampling_ratio);
-  int* work_counter = reinterpret_cast<int*>(tables + jdet_align_up((size_t)R * stride, 256));
-  {
-    const bool vec = input_nchw && ((H * W) & 3) == 0 && (C & 3) == 0 && ((((uintptr_t)input_nchw) | ((uintptr_t)nhwc_scratch)) & 15) == 0;
-    const int tiles_x = input_nchw ? jdet_ceil_div(H * W, vec ? kTileW : 32) : 0, tiles_y = input_nchw ? jdet_ceil_div(C, 32) : 0;
-    const int rows = input_nchw ? tiles_y * B : jdet_ceil_div(R, 1024);
-    if (rows > 65535) return cudaErrorInvalidConfiguration;
-    dim3 pgrid(tiles_x + jdet_ceil_div(R, rows), rows);
-    const size_t smem = std::max(stride + (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2), sizeof(float) * 32 * (kTileW + 1));
-    if (version == 1) {
-      if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-      roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)R, PH, PW, spatial_scale, sampling_ratio, tables, vec, work_counter);
-    } else {
-      if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-      roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)R, PH, PW, spatial_scale, sampling_ratio, tables, vec, work_counter);
-    }
+  const int Rt = with_tables ? R : 0;
+  const bool vec = input_nchw && ((H * W) & 3) == 0 && (C & 3) == 0 && ((((uintptr_t)input_nchw) | ((uintptr_t)nhwc_scratch)) & 15) == 0;
+  const int tiles_x = input_nchw ? jdet_ceil_div(H * W, vec ? kTileW : 32) : 0, tiles_y = input_nchw ? jdet_ceil_div(C, 32) : 0;
+  const int rows = input_nchw ? tiles_y * B : jdet_ceil_div(Rt, 1024);
+  if (rows > 65535) return cudaErrorInvalidConfiguration;
+  if (rows == 0) return cudaSuccess;
+  dim3 pgrid(tiles_x + jdet_ceil_div(Rt, rows), rows);
+  const size_t smem = std::max(stride + (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2), sizeof(float) * 32 * (kTileW + 1));
+  if (version == 1) {
+    if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
+    roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, L);
+  } else {
+    if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
+    roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, L);
   }
-  const float* nhwc = input_nchw ? nhwc_scratch : nhwc_in;
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_gather(const RoiLevels& L, const unsigned char* tables, int* work_counter, int C, int R, int PH, int PW,
+                                 int sampling_ratio, float* output, cudaStream_t st) {
+  const int nbins = PH * PW;
+  const size_t stride = roi_table_stride(nbins, sampling_ratio);
   const int slab = (C % 128 == 0) ? 128 : 64;
   const size_t smem = (((size_t)slab * (nbins | 1) + 3) & ~(size_t)3) * 4 + 2 * stride;
   const int nslabs = C / slab;
@@ -622,11 +654,26 @@ static cudaError_t launch_staged(int version, const float* input_nchw, const flo
 #define JDET_LAUNCH_ROI(QL_)                                                                                           \
   do {                                                                                                                 \
     if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_gather_kernel<QL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; } \
-    roi_gather_kernel<QL_><<<grid, 256, smem, st>>>(nhwc, tables, stride, C, H, W, nbins, nslabs, items, work_counter, output); \
+    roi_gather_kernel<QL_><<<grid, 256, smem, st>>>(L, tables, stride, C, nbins, nslabs, items, work_counter, output); \
   } while (0)
   if (slab == 128) JDET_LAUNCH_ROI(32); else JDET_LAUNCH_ROI(16);
 #undef JDET_LAUNCH_ROI
   return cudaGetLastError();
+}
+
+// single map: prologue (tables, + re-layout when `input_nchw` is given) and gather from the channel-last map
+static cudaError_t launch_staged(int version, const float* input_nchw, const float* nhwc_in, float* nhwc_scratch,
+                                 unsigned char* tables, const float* rois, int B, int C, int H, int W, int R, int PH, int PW,
+                                 float spatial_scale, int sampling_ratio, float* output, cudaStream_t st) {
+  const size_t stride = roi_table_stride(PH * PW, sampling_ratio);
+  int* work_counter = reinterpret_cast<int*>(tables + jdet_align_up((size_t)R * stride, 256));
+  RoiLevels L{};
+  L.n = 1;
+  L.lv[0] = RoiLevel{input_nchw ? nhwc_scratch : nhwc_in, H, W, spatial_scale};
+  cudaError_t e = launch_prologue(version, input_nchw, nhwc_scratch, B, C, H, W, true, tables, work_counter, rois, R, PH, PW,
+                                  sampling_ratio, L, st);
+  if (e != cudaSuccess) return e;
+  return launch_gather(L, tables, work_counter, C, R, PH, PW, sampling_ratio, output, st);
 }
 
 }  // namespace jdet
@@ -689,6 +736,50 @@ JDET_API int jdet_roi_align_rotated_nhwc(int version, const float* input_nhwc, i
     return JDET_ERR_WORKSPACE;
   return (int)launch_staged(version, nullptr, input_nhwc, nullptr, (unsigned char*)workspace, rois, B, C, H, W, R, PH, PW,
                             spatial_scale, sampling_ratio, output, (cudaStream_t)stream);
+}
+
+// Fused single-level-per-RoI extractor over FPN maps (OrientedSingleRoIExtractor / RboxSingleRoIExtractor.execute,
+// models/roi_extractors/oriented_single_level.py:91-114, rbox_single_level.py): level choice on the device, one
+// re-layout launch per level (the tap tables ride in the first), ONE gather over all RoIs writing final rows —
+// no boolean masks, no zero-filled output, no scatter-add.  feats/Hs/Ws/scales are HOST arrays of nlevels entries.
+JDET_API size_t jdet_roi_align_rotated_fpn_workspace_bytes(int nlevels, int B, int C, const int* Hs, const int* Ws, int R, int PH,
+                                                           int PW, int sampling_ratio) {
+  if (nlevels <= 0 || !Hs || !Ws || sampling_ratio <= 0 || PH <= 0 || PW <= 0) return 256;
+  size_t total = 0;
+  for (int l = 0; l < nlevels; l++) total += jdet_align_up((size_t)B * C * Hs[l] * Ws[l] * sizeof(float), 256);
+  return total + jdet_align_up((size_t)(R > 0 ? R : 0) * jdet::roi_table_stride(PH * PW, sampling_ratio), 256) + 256;
+}
+
+JDET_API int jdet_roi_align_rotated_fpn(int version, const float* const* feats, int nlevels, int B, int C, const int* Hs,
+                                        const int* Ws, const float* scales, const float* rois, int R, int PH, int PW,
+                                        int sampling_ratio, float ext_w, float ext_h, float rs_w, float rs_h, float finest_scale,
+                                        float* output, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace jdet;
+  if ((version != 0 && version != 1) || nlevels <= 0 || nlevels > kMaxLevels || !feats || !Hs || !Ws || !scales || B <= 0 || C <= 0 ||
+      R < 0 || PH <= 0 || PW <= 0)
+    return JDET_ERR_BAD_ARG;
+  if (R == 0) return 0;
+  if (!rois || !output) return JDET_ERR_BAD_ARG;
+  if (sampling_ratio <= 0 || C % 64 != 0 || (long long)PH * PW * sampling_ratio * sampling_ratio > kMaxSamples)
+    return JDET_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < jdet_roi_align_rotated_fpn_workspace_bytes(nlevels, B, C, Hs, Ws, R, PH, PW, sampling_ratio))
+    return JDET_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  RoiLevels L{};
+  L.n = nlevels; L.ext_w = ext_w; L.ext_h = ext_h; L.rs_w = rs_w; L.rs_h = rs_h; L.finest = finest_scale;
+  unsigned char* p = (unsigned char*)workspace;
+  for (int l = 0; l < nlevels; l++) {
+    if (!feats[l] || Hs[l] <= 0 || Ws[l] <= 0) return JDET_ERR_BAD_ARG;
+    L.lv[l] = RoiLevel{(const float*)p, Hs[l], Ws[l], scales[l]};
+    p += jdet_align_up((size_t)B * C * Hs[l] * Ws[l] * sizeof(float), 256);
+  }
+  unsigned char* tables = p;
+  int* work_counter = reinterpret_cast<int*>(tables + jdet_align_up((size_t)R * roi_table_stride(PH * PW, sampling_ratio), 256));
+  for (int l = 0; l < nlevels; l++)
+    JDET_RETURN_IF_CUDA(launch_prologue(version, feats[l], const_cast<float*>(L.lv[l].nhwc), B, C, Hs[l], Ws[l], l == 0, tables,
+                                        work_counter, rois, R, PH, PW, sampling_ratio, L, st));
+  JDET_RETURN_IF_CUDA(launch_gather(L, tables, work_counter, C, R, PH, PW, sampling_ratio, output, st));
+  return 0;
 }
 
 // backward of jdet_roi_align_rotated w.r.t. input: _RotatedROIAlign[_v1].grad (roi_align_rotated_v1.py:328-351,

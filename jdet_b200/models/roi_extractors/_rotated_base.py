@@ -61,3 +61,42 @@ class RotatedSingleLevelBase(nn.Module):
                 pooled.index_copy_(0, idx, self.roi_layers[level](feats[level], rois.index_select(0, idx)))
             start += n
         return pooled
+
+    # ---- fused path: one C-ABI call for the whole extractor (jdet_roi_align_rotated_fpn) -----------------------
+    def _fused(self, version, feats, rois, ext, rs):
+        """None when the fused kernel does not apply (autograd, non-fp32 / non-NCHW-contiguous maps, shapes it refuses);
+        the caller then runs the per-level path, which produces the same values."""
+        import ctypes
+        from ...ops._common import check, lib, scratch, stream_ptr
+        feats = list(feats)
+        f0 = feats[0]
+        if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
+            return None
+        if not (rois.is_cuda and rois.dtype == torch.float32 and rois.dim() == 2 and rois.shape[1] == 6):
+            return None
+        if any((not f.is_cuda) or f.dtype != torch.float32 or f.dim() != 4 or not f.is_contiguous() or f.device != f0.device
+               or f.shape[:2] != f0.shape[:2] for f in feats):
+            return None
+        layer = self.roi_layers[0]
+        ph, pw = pair(layer.output_size)
+        sr = int(layer.sampling_ratio)
+        n, (B, C), R = len(feats), f0.shape[:2], rois.shape[0]
+        out = torch.empty((R, C, ph, pw), dtype=torch.float32, device=f0.device)
+        if R == 0:
+            return out
+        r = rois.contiguous()
+        L = lib()
+        ptrs = (ctypes.c_void_p * n)(*[f.data_ptr() for f in feats])
+        Hs = (ctypes.c_int * n)(*[f.shape[2] for f in feats])
+        Ws = (ctypes.c_int * n)(*[f.shape[3] for f in feats])
+        sc = (ctypes.c_float * n)(*[float(l.spatial_scale) for l in self.roi_layers][:n])
+        with torch.cuda.device(f0.device):
+            ws = scratch(L.jdet_roi_align_rotated_fpn_workspace_bytes(n, B, C, Hs, Ws, R, ph, pw, sr), f0.device)
+            rc = L.jdet_roi_align_rotated_fpn(version, ptrs, n, B, C, Hs, Ws, sc, r.data_ptr(), R, ph, pw, sr,
+                                              float(ext[0]), float(ext[1]), float(rs[0]), float(rs[1]), float(self.finest_scale),
+                                              out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(f0.device))
+        if rc == -3:                # JDET_ERR_UNSUPPORTED
+            return None
+        check(rc, "roi_align_rotated_fpn")
+        return out
+

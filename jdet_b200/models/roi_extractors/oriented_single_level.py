@@ -25,6 +25,11 @@ class OrientedSingleRoIExtractor(RotatedSingleLevelBase):
     def forward(self, feats, rois, roi_scale_factor=None):
         if len(feats) == 1:
             return self.roi_layers[0](feats[0], rois)
+        fh, fw = pair(self.extend_factor)
+        sh, sw = (1., 1.) if roi_scale_factor is None else pair(roi_scale_factor)
+        fused = self._fused(1, feats, rois, (fw, fh), (sw, sh))        # one call: level choice, re-layouts, one gather
+        if fused is not None:
+            return fused
         stretched = self.roi_rescale(rois, self.extend_factor)
         lvls = self.map_roi_levels(stretched, len(feats))
         return self._pool_by_level(feats, self.roi_rescale(stretched, roi_scale_factor), lvls)

@@ -15,6 +15,9 @@ class RboxSingleRoIExtractor(RotatedSingleLevelBase):
     def forward(self, feats, rois):
         if len(feats) == 1:
             return self.roi_layers[0](feats[0], rois)
+        fused = self._fused(0, feats, rois, (1., 1.), (1., 1.))
+        if fused is not None:
+            return fused
         return self._pool_by_level(feats, rois, self.map_roi_levels(rois, len(feats)))
 
     execute = forward

@@ -507,8 +507,19 @@ def test_roi_extractor_and_iou_calculator():
         if (lvl == i).any():
             want[lvl == i] = oracle.roi_align_rotated(feats[i], r2[lvl == i], 7, 1 / s, 2, 1)
     assert np.abs(got - want).max() <= TOL
+    # the fused one-call path (jdet_roi_align_rotated_fpn) and the per-level path are the same kernels on the same tables
+    fc = [cu(f) for f in feats]
+    stretched = ext.roi_rescale(cu(rois), ext.extend_factor)
+    per_level = ext._pool_by_level(fc, stretched, ext.map_roi_levels(stretched, 4)).cpu().numpy()
+    assert np.array_equal(got, per_level)
     ext0 = RboxSingleRoIExtractor(dict(type="ROIAlignRotated", output_size=7, sampling_ratio=2), 64, strides)
-    assert ext0([cu(f) for f in feats], cu(rois)).shape == (400, 64, 7, 7)
+    got0 = ext0(fc, cu(rois)).cpu().numpy()
+    lvl0 = np.clip(np.floor(np.log2(np.sqrt(rois[:, 3] * rois[:, 4]) / 56 + 1e-6)), 0, 3).astype(int)
+    want0 = np.zeros_like(got0)
+    for i, s in enumerate(strides):
+        if (lvl0 == i).any():
+            want0[lvl0 == i] = oracle.roi_align_rotated(feats[i], rois[lvl0 == i], 7, 1 / s, 2, 0)
+    assert got0.shape == (400, 64, 7, 7) and np.abs(got0 - want0).max() <= TOL
     b = dota_boxes(rng, 50, 200.0)
     b6 = np.concatenate([b, rng.random((50, 1)).astype(np.float32)], 1)
     assert np.array_equal(BboxOverlaps2D_rotated()(cu(b6), cu(b)).cpu().numpy(), oracle.box_iou_rotated(b, b, 0))
