@@ -608,3 +608,29 @@ def test_oriented_rcnn_heads_forward():
         if sel.size:
             want = oracle.roi_align_rotated(feats[l].cpu().numpy(), r[sel], (7, 7), 1.0 / strides[l], 2, 1)
             assert np.abs(got[sel] - want).max() <= TOL
+
+
+@pytest.mark.gpu
+def test_ops_are_cuda_graph_capturable():
+    """no host sync / allocation inside the C-ABI calls — the ops can be captured in a CUDA graph and replayed."""
+    rng = np.random.default_rng(41)
+    x = cu(rng.standard_normal((1, 128, 48, 48)).astype(np.float32))
+    rois = cu(_rois(rng, 300, 1, 192.0, 8, 96))
+    b1, b2 = cu(dota_boxes(rng, 200, 300.0)), cu(dota_boxes(rng, 150, 300.0))
+    boxes = cu(s2anet_anchors(rng, 1, 48, 48, 8)[..., [1, 0, 2, 3, 4]].copy())
+    eager = (ops().roi_align_rotated_v1.roi_align(x, rois, (7, 7), 0.25, 2), ops().box_iou_rotated(b1, b2),
+             ops().fr.feature_refine(x, boxes, 1 / 8., 1))
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            cap = (ops().roi_align_rotated_v1.roi_align(x, rois, (7, 7), 0.25, 2), ops().box_iou_rotated(b1, b2),
+                   ops().fr.feature_refine(x, boxes, 1 / 8., 1))
+    for t in cap:
+        t.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(eager, cap):
+        assert torch.equal(a, b)
