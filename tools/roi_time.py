@@ -32,16 +32,6 @@ def t(fn, k=30):
     return tot / k * 1e3
 
 
-for spec in sys.argv[1:] or ["256"]:
-    parts = spec.split(",")           # threads[,slab[,carveout]]
-    os.environ["JDET_ROI_THREADS"] = parts[0]
-    for key, val in (("JDET_ROI_SLAB", parts[1] if len(parts) > 1 else ""), ("JDET_ROI_CARVEOUT", parts[2] if len(parts) > 2 else "")):
-        if val:
-            os.environ[key] = val
-        else:
-            os.environ.pop(key, None)
-    try:
-        print("threads,slab,carve", spec, "nchw %.1f us" % t(lambda: ops.roi_align_rotated_v1.roi_align(feat, rois, (7, 7), 0.25, 2)),
-              "channels_last %.1f us" % t(lambda: ops.roi_align_rotated_v1.roi_align(fcl, rois, (7, 7), 0.25, 2)), flush=True)
-    except Exception as e:  # noqa: BLE001
-        print("threads,slab,carve", spec, "failed:", e, flush=True)
+for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
+    print("nchw %.1f us" % t(lambda: ops.roi_align_rotated_v1.roi_align(feat, rois, (7, 7), 0.25, 2)),
+          "channels_last %.1f us" % t(lambda: ops.roi_align_rotated_v1.roi_align(fcl, rois, (7, 7), 0.25, 2)), flush=True)
