@@ -170,6 +170,23 @@ __global__ void __launch_bounds__(256, 2) feature_refine_bwd_kernel(const float*
 // stream with a short gather needs.  Centre reads and taps are then served from shared memory (lanes are
 // consecutive pixels: conflict-light); a sample whose taps leave the band falls back to global loads.
 // CTA = (row band, channel slab, image), one thread per pixel of the band.
+// the 1 or 5 sample points of a box (fr.py:128-153), decoded into taps
+template <int POINTS>
+__device__ __forceinline__ void fr_decode(const float* __restrict__ bb, float spatial_scale, int H, int W, Tap4 (&taps)[POINTS]) {
+  const float roi_y = __fmul_rn(__ldg(bb), spatial_scale), roi_x = __fmul_rn(__ldg(bb + 1), spatial_scale);
+  taps[0] = fr_tap(roi_y, roi_x, H, W);
+  if (POINTS > 1) {
+    const float rw = __fmul_rn(__ldg(bb + 2), spatial_scale), rh = __fmul_rn(__ldg(bb + 3), spatial_scale), ra = __ldg(bb + 4);
+    const float w2 = rw * 0.5f, h2 = rh * 0.5f;
+    const float ca = cosf(ra), sa = sinf(ra);
+    const float wx = __fmul_rn(ca, w2), wy = __fmul_rn(sa, w2), hx = __fmul_rn(-sa, h2), hy = __fmul_rn(ca, h2);
+    taps[1 % POINTS] = fr_tap(__fadd_rn(__fadd_rn(roi_y, wy), hy), __fadd_rn(__fadd_rn(roi_x, wx), hx), H, W);
+    taps[2 % POINTS] = fr_tap(__fadd_rn(__fsub_rn(roi_y, wy), hy), __fadd_rn(__fsub_rn(roi_x, wx), hx), H, W);
+    taps[3 % POINTS] = fr_tap(__fsub_rn(__fsub_rn(roi_y, wy), hy), __fsub_rn(__fsub_rn(roi_x, wx), hx), H, W);
+    taps[4 % POINTS] = fr_tap(__fsub_rn(__fadd_rn(roi_y, wy), hy), __fsub_rn(__fadd_rn(roi_x, wx), hx), H, W);
+  }
+}
+
 namespace fr_tma {
 
 constexpr int kHalo = 4;
@@ -177,15 +194,14 @@ constexpr int kMaxStages = 8;
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumers = kConsumerWarps * 32;
-constexpr int kPPT = 4;                            // pixels per consumer thread
-constexpr int kBandPixels = kConsumers * kPPT;     // 1024
 
-// points = 1.  CTA = 8 consumer warps + 1 producer warp; grid = (row bands, channel chunks, N).
-// A band is kBandPixels / W full-width rows (+ kHalo rows either side): contiguous in an NCHW plane, so one
-// cp.async.bulk per channel stages it.  The producer lane only waits on empty[] and issues copies; the
-// consumers never block on a refill, and `stages` channels per CTA x several CTAs per SM are in flight.
-// Each consumer thread owns kPPT pixels (same column group, rows kConsumers/W apart): taps and weights live
-// in registers for the whole channel walk; a pixel whose taps leave the staged rows reads them from global.
+// CTA = 8 consumer warps + 1 producer warp; grid = (row bands, channel chunks, N).  A band is 256*PPT / W
+// full-width rows (+ kHalo rows either side): contiguous in an NCHW plane, so one cp.async.bulk per channel
+// stages it.  The producer lane only waits on empty[] and issues copies; the consumers never block on a
+// refill, and `stages` channels per CTA x several CTAs per SM are in flight.  Each consumer thread owns PPT
+// pixels (rows 256/W apart): their POINTS tap sets and weights live in registers for the whole channel walk
+// (points = 1: PPT = 4; points = 5: PPT = 2); a sample whose taps leave the staged rows reads them from global.
+template <int POINTS, int PPT>
 __global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_kernel(const float* __restrict__ feat,
                                                                              const float* __restrict__ boxes, int C, int H,
                                                                              int W, float spatial_scale, int rows_per_band,
@@ -225,24 +241,29 @@ __global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_kernel(con
   }
 
   // ---- consumers: this thread's pixels and their taps (band-relative offsets when every corner is staged)
-  Tap4 taps[kPPT];
-  int pc[kPPT];                                                    // centre, band-relative; -1: pixel not in the map
-  bool staged[kPPT];
+  Tap4 taps[PPT][POINTS];
+  int pc[PPT];                                                     // centre, band-relative; -1: pixel not in the map
+  unsigned staged[PPT];                                            // bit i: sample i reads the smem band
   const int blo = lo * W, bhi = hi * W;
   const int band_px = min(rows_per_band, H - r0) * W;
 #pragma unroll
-  for (int j = 0; j < kPPT; j++) {
+  for (int j = 0; j < PPT; j++) {
     const int i = tid + j * kConsumers;                            // pixel index inside the band
     pc[j] = -1;
-    staged[j] = false;
-    taps[j].o00 = -1;
+    staged[j] = 0u;
+#pragma unroll
+    for (int k = 0; k < POINTS; k++) taps[j][k].o00 = -1;
     if (i < band_px) {
       const int p = r0 * W + i;
-      const float* bb = boxes + ((size_t)n * HW + p) * 5;
-      Tap4 t = fr_tap(__fmul_rn(__ldg(bb), spatial_scale), __fmul_rn(__ldg(bb + 1), spatial_scale), H, W);
-      staged[j] = t.o00 >= blo && t.o11 < bhi;                     // o00 is the smallest, o11 the largest offset
-      if (staged[j]) { t.o00 -= blo; t.o01 -= blo; t.o10 -= blo; t.o11 -= blo; }
-      taps[j] = t;
+      fr_decode<POINTS>(boxes + ((size_t)n * HW + p) * 5, spatial_scale, H, W, taps[j]);
+#pragma unroll
+      for (int k = 0; k < POINTS; k++) {
+        Tap4& t = taps[j][k];
+        if (t.o00 >= blo && t.o11 < bhi) {                         // o00 is the smallest, o11 the largest offset
+          staged[j] |= 1u << k;
+          t.o00 -= blo; t.o01 -= blo; t.o10 -= blo; t.o11 -= blo;
+        }
+      }
       pc[j] = p - blo;
     }
   }
@@ -253,20 +274,23 @@ __global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_kernel(con
   for (int c = 0; c < nch; c++) {
     mbar_wait(&full[stage], phase);
     const float* sp = ring + (size_t)stage * stage_elems;
-    float v[kPPT];
+    float v[PPT];
 #pragma unroll
-    for (int j = 0; j < kPPT; j++) {
-      const Tap4& t = taps[j];
+    for (int j = 0; j < PPT; j++) {
       v[j] = 0.f;
       if (pc[j] >= 0) {
         v[j] = sp[pc[j]];
-        if (staged[j]) v[j] += t.w1 * sp[t.o00] + t.w2 * sp[t.o01] + t.w3 * sp[t.o10] + t.w4 * sp[t.o11];
-        else if (t.o00 >= 0)
-          v[j] += t.w1 * __ldg(gplane + t.o00) + t.w2 * __ldg(gplane + t.o01) + t.w3 * __ldg(gplane + t.o10) + t.w4 * __ldg(gplane + t.o11);
+#pragma unroll
+        for (int k = 0; k < POINTS; k++) {
+          const Tap4& t = taps[j][k];
+          if (staged[j] >> k & 1u) v[j] += t.w1 * sp[t.o00] + t.w2 * sp[t.o01] + t.w3 * sp[t.o10] + t.w4 * sp[t.o11];
+          else if (t.o00 >= 0)
+            v[j] += t.w1 * __ldg(gplane + t.o00) + t.w2 * __ldg(gplane + t.o01) + t.w3 * __ldg(gplane + t.o10) + t.w4 * __ldg(gplane + t.o11);
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < kPPT; j++)
+    for (int j = 0; j < PPT; j++)
       if (pc[j] >= 0) st_stream(dst + pc[j], v[j]);
     __syncwarp();                                                  // every lane issued its stores, so its smem reads returned
     if (lane == 0) mbar_arrive(&empty[stage]);
@@ -291,13 +315,16 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W;
   // TMA-staged path: full-width row bands (contiguous in NCHW), one thread per pixel of the band
-  // (measured on B200, cfg4: points=1 TMA ring 0.196 ms vs vec4 gather 0.203 ms; points=5 TMA ring 0.82 ms vs
-  //  register gather 0.68 ms — five sample sets per pixel make the smem tap reads, not the global stream, the cost)
-  if (points == 1 && W % 4 == 0 && W <= fr_tma::kBandPixels && ((uintptr_t)features & 15) == 0) {
+  // TMA-staged path: full-width row bands (contiguous in NCHW)
+  // (measured on B200, cfg4: points = 1: 0.130 ms vs 0.203 ms for the 16-B-vector register gather; points = 5 with
+  //  PPT = 2 (110 registers, 2 CTAs/SM): 1.14 ms vs 0.68 ms for the register gather — 21 dependent smem reads per
+  //  pixel-channel on 16 warps per SM are latency-bound, so points = 5 stays on feature_refine_kernel<5>)
+  const int band_pixels = fr_tma::kConsumers * 4;
+  if (points == 1 && W % 4 == 0 && W <= band_pixels && ((uintptr_t)features & 15) == 0) {
     using namespace fr_tma;
-    const int rows = max(1, min(H, kBandPixels / W));
+    const int rows = max(1, min(H, band_pixels / W));
     const int stage_elems = (rows + 2 * kHalo) * W;
-    int stages = (int)((64 * 1024) / ((size_t)stage_elems * 4));   // ~64 KB of copies in flight per CTA, 3 CTAs per SM
+    int stages = (int)((64 * 1024) / ((size_t)stage_elems * 4));   // ~64 KB of copies in flight per CTA
     stages = stages > kMaxStages ? kMaxStages : stages;
     if (stages >= 2) {
       const int bands = jdet_ceil_div(H, rows);
@@ -305,10 +332,15 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
       while (cpc > 4 * stages && (long long)bands * jdet_ceil_div(C, cpc) * N < 148 * 6) cpc = (cpc + 1) / 2;
       const size_t smem = (size_t)stages * stage_elems * 4 + 2 * kMaxStages * sizeof(uint64_t);
       dim3 g(bands, jdet_ceil_div(C, cpc), N);
-      JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      // without this the driver picks the smallest carve-out that fits ONE block (ncu: occupancy_limit_shared_mem = 1)
-      JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      feature_refine_tma_kernel<<<g, kConsumers + 32, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output);
+#define JDET_LAUNCH_FR_TMA(P, T)                                                                                       \
+  do {                                                                                                                 \
+    JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    /* without this the driver picks the smallest carve-out that fits ONE block (ncu: occupancy_limit_shared_mem = 1) */ \
+    JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<P, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+    feature_refine_tma_kernel<P, T><<<g, kConsumers + 32, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output); \
+  } while (0)
+      JDET_LAUNCH_FR_TMA(1, 4);
+#undef JDET_LAUNCH_FR_TMA
       return (int)cudaGetLastError();
     }
   }
