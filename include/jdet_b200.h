@@ -38,6 +38,11 @@ size_t jdet_box_iou_rotated_workspace_bytes(int n1, int n2);
 int jdet_box_iou_rotated(const float* boxes1, int n1, const float* boxes2, int n2, float* ious, int version,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* same op with the arithmetic of the reference's CPU build selectable: arithmetic 1 = CUDA build (== the call above),
+ * 0 = CPU build, i.e. the cpu_src path of ops/box_iou_rotated.py:487-500 (std::sort hull :316-325), bit for bit.   */
+int jdet_box_iou_rotated_ex(const float* boxes1, int n1, const float* boxes2, int n2, float* ious, int version,
+                            int arithmetic, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- nms_rotated -----------------------------------------------------------------------------
  * replaces: nms_rotated_cuda(dets, order_t, iou_threshold, box_length) ops/nms_rotated.py:506-513
  *           (kernel :352-411, launch + host reduce :450-493).
@@ -47,6 +52,12 @@ int jdet_box_iou_rotated(const float* boxes1, int n1, const float* boxes2, int n
 size_t jdet_nms_rotated_workspace_bytes(int n, int box_length);
 int jdet_nms_rotated(const float* dets, int n, int box_length, const int* order, float iou_threshold,
                      unsigned char* keep, void* workspace, size_t workspace_bytes, void* stream);
+
+/* same op with the reference's CPU-path convention selectable: convention 1 = nms_rotated_cuda (== the call above);
+ * 0 = nms_rotated_cpu ops/nms_rotated.py:495-504 (loop :414-449): suppress on IoU >= thr, CPU-build IoU arithmetic.
+ * This is what the tile -> image merge (data/devkits/result_merge.py:132-145 py_cpu_nms_obb) runs.                 */
+int jdet_nms_rotated_ex(const float* dets, int n, int box_length, const int* order, float iou_threshold, int convention,
+                        unsigned char* keep, void* workspace, size_t workspace_bytes, void* stream);
 
 /* stable descending argsort (ties: lower index first)
  * replaces: scores.argsort(0, descending=True) ops/nms_rotated.py:519,532                          */

@@ -24,8 +24,10 @@ SIGNATURES = {
     "jdet_version": (ctypes.c_char_p, []),
     "jdet_box_iou_rotated_workspace_bytes": (_sz, [_i, _i]),
     "jdet_box_iou_rotated": (_i, [_p, _i, _p, _i, _p, _i, _p, _sz, _p]),
+    "jdet_box_iou_rotated_ex": (_i, [_p, _i, _p, _i, _p, _i, _i, _p, _sz, _p]),
     "jdet_nms_rotated_workspace_bytes": (_sz, [_i, _i]),
     "jdet_nms_rotated": (_i, [_p, _i, _i, _p, _f, _p, _p, _sz, _p]),
+    "jdet_nms_rotated_ex": (_i, [_p, _i, _i, _p, _f, _i, _p, _p, _sz, _p]),
     "jdet_argsort_desc_workspace_bytes": (_sz, [_i]),
     "jdet_argsort_desc": (_i, [_p, _i, _p, _p, _sz, _p]),
     "jdet_roi_align_rotated_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),

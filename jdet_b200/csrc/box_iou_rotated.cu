@@ -40,7 +40,7 @@ template <int VERSION, bool VEC4>
 __global__ void __launch_bounds__(kThreads) iou_tile_kernel(const BoxRec* __restrict__ rec1, int n1,
                                                              const BoxRec* __restrict__ rec2, int n2,
                                                              float* __restrict__ out, int* __restrict__ gcount,
-                                                             uint2* __restrict__ gqueue, int gcap) {
+                                                             uint2* __restrict__ gqueue, int gcap, int variant) {
   __shared__ BoxRec s_row[kTR];
   __shared__ BoxRec s_col[kTC];
   __shared__ __align__(16) float s_cx[kTC], s_cy[kTC], s_cr[kTC];
@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(kThreads) iou_tile_kernel(const BoxRec* __rest
       const int r = e >> 7, c = e & 127;
       const BoxRec& A = s_row[r];
       const BoxRec& B = s_col[c];
-      out[(size_t)(row0 + r) * n2 + (col0 + c)] = (A.tag == 0.f && B.tag == 0.f) ? iou_exact<VERSION>(A, B) : 0.f;
+      out[(size_t)(row0 + r) * n2 + (col0 + c)] =
+          (A.tag == 0.f && B.tag == 0.f) ? (variant ? iou_exact<VERSION, 1>(A, B) : iou_exact<VERSION, 0>(A, B)) : 0.f;
     }
   }
 }
@@ -170,13 +171,14 @@ template <int VERSION>
 __global__ void __launch_bounds__(256) iou_exact_kernel(const BoxRec* __restrict__ rec1, const BoxRec* __restrict__ rec2,
                                                          int n2, const int* __restrict__ gcount,
                                                          const uint2* __restrict__ gqueue, int gcap,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, int variant) {
   const int total = min(*gcount, gcap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint2 e = gqueue[i];
     if (e.x == 0xffffffffu) continue;
     const BoxRec A = rec1[e.x], B = rec2[e.y];
-    out[(size_t)e.x * n2 + e.y] = (A.tag == 0.f && B.tag == 0.f) ? iou_exact<VERSION>(A, B) : 0.f;
+    out[(size_t)e.x * n2 + e.y] =
+        (A.tag == 0.f && B.tag == 0.f) ? (variant ? iou_exact<VERSION, 1>(A, B) : iou_exact<VERSION, 0>(A, B)) : 0.f;
   }
 }
 
@@ -201,10 +203,21 @@ JDET_API size_t jdet_box_iou_rotated_workspace_bytes(int n1, int n2) {
 // version 0: jdet.ops.box_iou_rotated      (ops/box_iou_rotated.py:502-509)
 // version 1: jdet.ops.box_iou_rotated_v1   (ops/box_iou_rotated_v1.py:507-525, incl. small-box zeroing)
 // boxes1 (n1,5), boxes2 (n2,5), ious (n1,n2): device, fp32, contiguous.  Never syncs, never allocates.
+JDET_API int jdet_box_iou_rotated_ex(const float* boxes1, int n1, const float* boxes2, int n2, float* ious, int version,
+                                     int arithmetic, void* workspace, size_t workspace_bytes, void* stream);
+
 JDET_API int jdet_box_iou_rotated(const float* boxes1, int n1, const float* boxes2, int n2, float* ious,
                                   int version, void* workspace, size_t workspace_bytes, void* stream) {
+  return jdet_box_iou_rotated_ex(boxes1, n1, boxes2, n2, ious, version, /*arithmetic=*/1, workspace, workspace_bytes, stream);
+}
+
+// arithmetic 1: the reference's CUDA build (exchange-sort hull) — what jdet_box_iou_rotated computes;
+// arithmetic 0: its CPU build (std::sort hull with the stale dist[] of box_iou_rotated.py:219-224), bit for bit.
+JDET_API int jdet_box_iou_rotated_ex(const float* boxes1, int n1, const float* boxes2, int n2, float* ious, int version,
+                                     int arithmetic, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace jdet;
-  if (n1 < 0 || n2 < 0 || (version != 0 && version != 1)) return JDET_ERR_BAD_ARG;
+  if (n1 < 0 || n2 < 0 || (version != 0 && version != 1) || (arithmetic != 0 && arithmetic != 1)) return JDET_ERR_BAD_ARG;
+  const int variant = arithmetic;
   if (n1 == 0 || n2 == 0) return 0;
   if (!boxes1 || !boxes2 || !ious) return JDET_ERR_BAD_ARG;
   if (workspace_bytes < jdet_box_iou_rotated_workspace_bytes(n1, n2) || !workspace) return JDET_ERR_WORKSPACE;
@@ -223,13 +236,13 @@ JDET_API int jdet_box_iou_rotated(const float* boxes1, int n1, const float* boxe
   const long long pairs = (long long)n1 * n2;
   const int xgrid = (int)(pairs < 256 * 1024 ? (pairs + 255) / 256 : kNumSMs * 8);
   if (version == 0) {
-    if (vec) iou_tile_kernel<0, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap);
-    else     iou_tile_kernel<0, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap);
-    iou_exact_kernel<0><<<xgrid, 256, 0, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious);
+    if (vec) iou_tile_kernel<0, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
+    else     iou_tile_kernel<0, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
+    iou_exact_kernel<0><<<xgrid, 256, 0, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious, variant);
   } else {
-    if (vec) iou_tile_kernel<1, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap);
-    else     iou_tile_kernel<1, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap);
-    iou_exact_kernel<1><<<xgrid, 256, 0, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious);
+    if (vec) iou_tile_kernel<1, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
+    else     iou_tile_kernel<1, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
+    iou_exact_kernel<1><<<xgrid, 256, 0, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious, variant);
   }
   return (int)cudaGetLastError();
 }

@@ -22,6 +22,7 @@
 // before j, IoU arguments in (higher, lower) order, label column compared with != first.
 #include <cub/cub.cuh>
 
+#include <math.h>
 #include "common.cuh"
 #include "rbox_geom.cuh"
 
@@ -143,8 +144,10 @@ __device__ __forceinline__ long long tri_index(long long rb, long long cb) { ret
 __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     const BoxRec* __restrict__ rec, const int* __restrict__ seg_start, const int* __restrict__ item_base,
     const long long* __restrict__ tile_base, const int* __restrict__ scan, int n, float thr,
-    int label_in_pair, int* __restrict__ counter, unsigned long long* __restrict__ mask,
+    int flags, int* __restrict__ counter, unsigned long long* __restrict__ mask,
     uint4* __restrict__ xqueue, int xcap) {
+  const int label_in_pair = flags & 1;       // thr < 0 corner: single segment, label mismatch => IoU 0
+  const bool cpu_arith = (flags & 2) != 0;   // the reference CPU build's hull sort; no IoU-upper-bound pruning (its IoU is not bounded by the true one)
   extern __shared__ __align__(16) unsigned char s_dyn[];
   BoxRec* s_row = reinterpret_cast<BoxRec*>(s_dyn);                       //  2 KB
   BoxRec* s_col = s_row + 64;                                             // 16 KB
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
           const BoxRec& A = s_row[(e >> 6) & 63];
           const BoxRec& B = s_col[(e >> 12) * 64 + (e & 63)];
           // SAT reject, then the IoU upper bound: a pair that provably cannot exceed thr never reaches phase 3
-          keep = label_in_pair ? true : (A.tag == B.tag && !sat_disjoint<0>(A, B) && !(iou_upper_bound<0>(A, B) < thr));
+          keep = label_in_pair ? true : (A.tag == B.tag && !sat_disjoint<0>(A, B) && (cpu_arith || !(iou_upper_bound<0>(A, B) < thr)));
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (bal) {
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
           const BoxRec& B = s_col[tt * 64 + cc];
           float v;
           if (label_in_pair && A.tag != B.tag) v = 0.f;   // nms_rotated.py:285-286
-          else v = iou_exact<0>(A, B);
+          else v = cpu_arith ? iou_exact<0, 0>(A, B) : iou_exact<0, 1>(A, B);
           if (v > thr) atomicOr(&s_bits[(tt * 64 + r) * 2 + (cc >> 5)], 1u << (cc & 31));
         }
       }
@@ -332,7 +335,9 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
 // bit set with a 64-bit atomicOr straight into the triangular mask written (as zeros) by the mask kernel.
 __global__ void __launch_bounds__(256) nms_exact_kernel(const BoxRec* __restrict__ rec, const int* __restrict__ counter,
                                                          const uint4* __restrict__ xqueue, int xcap, float thr,
-                                                         int label_in_pair, unsigned long long* __restrict__ mask) {
+                                                         int flags, unsigned long long* __restrict__ mask) {
+  const int label_in_pair = flags & 1;
+  const bool cpu_arith = (flags & 2) != 0;
   const int total = min(counter[1], xcap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint4 e = xqueue[i];
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(256) nms_exact_kernel(const BoxRec* __restrict
     const BoxRec A = rec[e.x], B = rec[e.y];
     float v;
     if (label_in_pair && A.tag != B.tag) v = 0.f;
-    else v = iou_exact<0>(A, B);
+    else v = cpu_arith ? iou_exact<0, 0>(A, B) : iou_exact<0, 1>(A, B);
     if (v > thr) {
       const unsigned long long word = ((unsigned long long)(e.w >> 8) << 32) | e.z;
       atomicOr(mask + word, 1ull << (e.w & 63u));
@@ -449,10 +454,23 @@ JDET_API size_t jdet_nms_rotated_workspace_bytes(int n, int box_length) {
 // dets (n, box_length) fp32, box_length in {5,6}: [x,y,w,h,theta(,label)]; order (n,) int32 = indices
 // by descending score; keep (n,) bytes, written in full (1 = kept), indexed like dets.
 // == nms_rotated_cuda(dets, order_t, iou_threshold, box_length), ops/nms_rotated.py:506-513.
+JDET_API int jdet_nms_rotated_ex(const float* dets, int n, int box_length, const int* order, float iou_threshold, int convention,
+                                 unsigned char* keep, void* workspace, size_t workspace_bytes, void* stream);
+
 JDET_API int jdet_nms_rotated(const float* dets, int n, int box_length, const int* order, float iou_threshold,
                               unsigned char* keep, void* workspace, size_t workspace_bytes, void* stream) {
+  return jdet_nms_rotated_ex(dets, n, box_length, order, iou_threshold, /*convention=*/1, keep, workspace, workspace_bytes, stream);
+}
+
+// convention 1: nms_rotated_cuda (ops/nms_rotated.py:506-513) — suppress on IoU > thr, CUDA-build IoU arithmetic.
+// convention 0: nms_rotated_cpu  (ops/nms_rotated.py:495-504, loop :414-449) — suppress on IoU >= thr with the CPU build's
+//               IoU arithmetic (std::sort hull).  In fp32 `x >= t` is `x > pred(t)`; the greedy loop's result equals the
+//               mask-and-scan's (a box is suppressed iff a KEPT higher-ranked box overlaps it).
+JDET_API int jdet_nms_rotated_ex(const float* dets, int n, int box_length, const int* order, float iou_threshold, int convention,
+                                 unsigned char* keep, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace jdet;
-  if (n < 0 || (box_length != 5 && box_length != 6)) return JDET_ERR_BAD_ARG;
+  if (n < 0 || (box_length != 5 && box_length != 6) || (convention != 0 && convention != 1)) return JDET_ERR_BAD_ARG;
+  if (convention == 0) iou_threshold = nextafterf(iou_threshold, -INFINITY);
   if (n == 0) return 0;
   if (!dets || !order || !keep || !workspace) return JDET_ERR_BAD_ARG;
   if (n > 1500000) return JDET_ERR_UNSUPPORTED;      // scan kernel keeps ceil(n/64) words in smem
@@ -461,6 +479,7 @@ JDET_API int jdet_nms_rotated(const float* dets, int n, int box_length, const in
   cudaStream_t st = (cudaStream_t)stream;
   const int T = 256, G = jdet_ceil_div(n + 1, T);
   const int label_in_pair = (iou_threshold < 0.f) ? 1 : 0;   // cross-class pairs then DO suppress (0 > thr)
+  const int flags = label_in_pair | (convention == 0 ? 2 : 0);
   const bool segment = (box_length == 6) && !label_in_pair;
 
   JDET_RETURN_IF_CUDA(cudaMemsetAsync(keep, 0, (size_t)n, st));
@@ -496,9 +515,9 @@ JDET_API int jdet_nms_rotated(const float* dets, int n, int box_length, const in
   const size_t mask_smem = (size_t)(64 + kCH * 64) * sizeof(BoxRec) + 64 * 16 + (size_t)kCH * 64 * 2 * 4 + (size_t)kQCap * 2 * 2;
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_smem));
   nms_mask_kernel<<<kNumSMs * 3, kMaskThreads, mask_smem, st>>>(w.rec, w.seg_start, w.item_base, w.tile_base,
-                                                        w.flag_scan, n, iou_threshold, label_in_pair,
+                                                        w.flag_scan, n, iou_threshold, flags,
                                                         w.counters, w.mask, w.xqueue, w.xcap);
-  nms_exact_kernel<<<kNumSMs * 8, 256, 0, st>>>(w.rec, w.counters, w.xqueue, w.xcap, iou_threshold, label_in_pair, w.mask);
+  nms_exact_kernel<<<kNumSMs * 8, 256, 0, st>>>(w.rec, w.counters, w.xqueue, w.xcap, iou_threshold, flags, w.mask);
   const size_t smem = (size_t)jdet_ceil_div(n, 64) * 8;
   if (smem > 48 * 1024)
     JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -29,9 +29,7 @@ def argsort_desc(scores):
     return order
 
 
-def nms_rotated_cuda(dets, order_t, iou_threshold, box_length=6):
-    """keep mask (n,) bool.  dets (n, box_length): [x,y,w,h,theta(,label)]; order_t: indices by
-    descending score.  Strict `IoU > iou_threshold`, as the reference CUDA kernel (:403-404)."""
+def _nms_keep(dets, order_t, iou_threshold, box_length, convention):
     require_cuda(dets, order_t)
     d = f32c(dets)
     assert d.dim() == 2 and d.shape[1] == box_length and box_length in (5, 6)
@@ -44,14 +42,35 @@ def nms_rotated_cuda(dets, order_t, iou_threshold, box_length=6):
     L = lib()
     with torch.cuda.device(d.device):
         ws = scratch(L.jdet_nms_rotated_workspace_bytes(n, box_length), d.device)
-        check(L.jdet_nms_rotated(d.data_ptr(), n, box_length, order.data_ptr(), float(iou_threshold),
-                                 keep.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(d.device)), "nms_rotated")
+        check(L.jdet_nms_rotated_ex(d.data_ptr(), n, box_length, order.data_ptr(), float(iou_threshold), convention,
+                                    keep.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(d.device)), "nms_rotated")
     return keep
 
 
+def nms_rotated_cuda(dets, order_t, iou_threshold, box_length=6):
+    """keep mask (n,) bool.  dets (n, box_length): [x,y,w,h,theta(,label)]; order_t: indices by
+    descending score.  Strict `IoU > iou_threshold`, as the reference CUDA kernel (:403-404)."""
+    return _nms_keep(dets, order_t, iou_threshold, box_length, 1)
+
+
 def nms_rotated_cpu(dets, order_t, iou_threshold, box_length=6):
-    raise NotImplementedError("jdet_b200 has no CPU path (the reference's is ops/nms_rotated.py:495-504); "
-                              "use nms_rotated_cuda")
+    """The reference's CPU path (ops/nms_rotated.py:495-504, loop :414-449) — suppress on `IoU >= thr`, IoU with the
+    CPU build's std::sort hull — evaluated on the GPU, bit for bit (jdet_nms_rotated_ex, convention 0).  The two
+    reference builds can disagree by far more than rounding on the same pair (the CPU build reads stale distances after
+    its sort, box_iou_rotated.py:219-224), so the arithmetic is selectable, not just the comparison.  No host path."""
+    return _nms_keep(dets, order_t, iou_threshold, box_length, 0)
+
+
+def py_cpu_nms_obb(dets, thresh):
+    """Tile -> image merge NMS (data/devkits/result_merge.py:132-145): dets (n,9) = 4 corner points + score ->
+    indices kept, ascending.  The reference converts polygons with cv2.minAreaRect; detections here are rectangles
+    produced by obb2poly / rotated_box_to_poly, so the closed-form rectpoly2obb is used instead."""
+    from ..models.boxes.coder import rectpoly2obb
+    if dets.numel() == 0:
+        return torch.zeros((0,), dtype=torch.int64, device=dets.device)
+    boxes = rectpoly2obb(dets[:, :8].float())
+    order = argsort_desc(dets[:, 8].float().contiguous())
+    return torch.where(nms_rotated_cpu(boxes, order, thresh, box_length=5))[0]
 
 
 def ml_nms_rotated(dets, scores, labels, iou_threshold):

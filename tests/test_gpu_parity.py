@@ -634,3 +634,69 @@ def test_ops_are_cuda_graph_capturable():
     torch.cuda.synchronize()
     for a, b in zip(eager, cap):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("thr", [0.1, 0.3, 0.0])
+def test_nms_rotated_cpu_convention_on_gpu(thr):
+    """the reference CPU path suppresses on IoU >= thr (nms_rotated.py:444).  The GPU mirror
+    runs the same kernel with the threshold one ulp lower; checked against the oracle's CPU-convention NMS (std::sort hull
+    variant of the IoU, `>=`) on clustered boxes with labels, and through the tile-merge wrapper py_cpu_nms_obb."""
+    rng = np.random.default_rng(53)
+    n = 3000
+    d = clustered_boxes(rng, n, 25, 500.0)
+    lab = rng.integers(0, 4, n).astype(np.float32)
+    s = tie_free_scores(rng, n)
+    d6 = np.concatenate([d, lab[:, None]], 1)
+    order = oracle.argsort_desc(s)
+    want = oracle.nms_rotated_keep(d6, order, thr, oracle.VARIANT_CPU)
+    got = ops().nms_rotated.nms_rotated_cpu(cu(d6), cu(order, torch.int32), thr, 6).cpu().numpy()
+    assert np.array_equal(got, want)
+    if thr > 0:
+        strict = ops().nms_rotated.nms_rotated_cuda(cu(d6), cu(order, torch.int32), thr, 6).cpu().numpy()
+        assert strict.sum() >= got.sum()                      # ">" never suppresses more than ">="
+        from jdet_b200.models.boxes import obb2poly, rectpoly2obb
+        polys = obb2poly(cu(d))
+        keep = ops().nms_rotated.py_cpu_nms_obb(torch.cat([polys, cu(s)[:, None]], 1), thr).cpu().numpy()
+        boxes5 = rectpoly2obb(polys).cpu().numpy()
+        want5 = np.nonzero(oracle.nms_rotated_keep(boxes5, order, thr, oracle.VARIANT_CPU))[0]
+        assert np.array_equal(keep, want5)
+
+
+@pytest.mark.gpu
+def test_iou_cpu_build_arithmetic_bit_exact():
+    """SURVEY 8a rows a1/a5: the reference's CPU build sorts the hull with std::sort (box_iou_rotated.py:316-325) and keeps
+    stale distances afterwards (:219-224).  jdet_box_iou_rotated_ex(arithmetic=0) restates that on the GPU: bit-equal to the
+    golden vectors produced by the reference's own compiled cpu_src, and to the oracle's CPU variant on random, clustered,
+    adversarial and many-vertex (shared corners, 45-degree copies: up to 24 hull points -> the introsort branch) inputs."""
+    g = np.load(os.path.join(GOLD, "ref_cpu_iou.npz"))
+    got = ops().box_iou_rotated(cu(g["boxes1"]), cu(g["boxes2"]), cpu_arithmetic=True).cpu().numpy()
+    assert np.array_equal(bits(got), bits(g["iou_v0_cpu"]))
+    rng = np.random.default_rng(61)
+    star = []
+    for w, h in ((10, 10), (10, 4), (7, 7), (12, 3)):
+        for k in range(8):
+            star.append([50, 50, w, h, k * np.pi / 4])
+            star.append([50 + (k % 3) * 0.5 * w, 50, w, h, k * np.pi / 8])
+            star.append([50, 50 + 0.5 * h, w, h, -k * np.pi / 4])
+    star = np.asarray(star, np.float32)
+    sets = [(dota_boxes(rng, 300, 200.0), dota_boxes(rng, 280, 200.0)), (clustered_boxes(rng, 256, 8, 100.0),) * 2,
+            (np.asarray(ADVERSARIAL, np.float32),) * 2, (star, star)]
+    ndiff = 0
+    for b1, b2 in sets:
+        got = ops().box_iou_rotated(cu(b1), cu(b2), cpu_arithmetic=True).cpu().numpy()
+        want = oracle.box_iou_rotated(b1, b2, 0, oracle.VARIANT_CPU)
+        assert np.array_equal(bits(got), bits(want))
+        ndiff += int((want != oracle.box_iou_rotated(b1, b2, 0, oracle.VARIANT_CUDA)).sum())
+    assert ndiff > 0          # the two reference builds really do differ on these inputs (else the test proves nothing)
+
+
+@pytest.mark.gpu
+def test_nms_cpu_path_golden():
+    """nms_rotated_cpu on the GPU == the reference's compiled CPU NMS (golden keep masks, thr 0.1/0.3/0.5, 5 and 6 columns)."""
+    g = np.load(os.path.join(GOLD, "ref_cpu_nms.npz"))
+    d6, order = g["dets6"], cu(g["order"], torch.int32)
+    for thr in (0.1, 0.3, 0.5):
+        for bl, d in ((5, d6[:, :5]), (6, d6)):
+            keep = ops().nms_rotated.nms_rotated_cpu(cu(d), order, thr, box_length=bl).cpu().numpy()
+            assert np.array_equal(keep, g["keep%d_cpu_thr%02d" % (bl, int(thr * 10))])
