@@ -28,12 +28,21 @@ namespace jdet {
 constexpr int kTR = 64, kTC = 128, kThreads = 256;
 
 // tag handling: IoU has no labels; tag = 1.0f marks a forced-zero box (v1 small-box post pass).
-__global__ void __launch_bounds__(256) rec_kernel(const float* __restrict__ boxes, int n, int stride,
-                                                  int zero_small, BoxRec* __restrict__ rec) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* b = boxes + (size_t)i * stride;
-  rec[i] = make_rec(b[0], b[1], b[2], b[3], b[4], 0.f, zero_small != 0, false);
+// both box sets in one launch (small problems are launch-bound); also resets the candidate counter
+__global__ void __launch_bounds__(256) rec_kernel(const float* __restrict__ boxes1, int n1, const float* __restrict__ boxes2,
+                                                  int n2, int zero_small, BoxRec* __restrict__ rec1,
+                                                  BoxRec* __restrict__ rec2, int* __restrict__ gcount) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *gcount = 0;
+  const float* b;
+  BoxRec* dst;
+  if (i < n1) { b = boxes1 + (size_t)i * 5; dst = rec1 + i; }
+  else {
+    i -= n1;
+    if (i >= n2) return;
+    b = boxes2 + (size_t)i * 5; dst = rec2 + i;
+  }
+  *dst = make_rec(b[0], b[1], b[2], b[3], b[4], 0.f, zero_small != 0, false);
 }
 
 template <int VERSION, bool VEC4>
@@ -228,9 +237,7 @@ JDET_API int jdet_box_iou_rotated_ex(const float* boxes1, int n1, const float* b
   int* gcount = (int*)wsp;                     wsp += 256;
   uint2* gqueue = (uint2*)wsp;
   const int gcap = (int)iou_queue_cap(n1, n2);
-  JDET_RETURN_IF_CUDA(cudaMemsetAsync(gcount, 0, 256, st));
-  rec_kernel<<<jdet_ceil_div(n1, 256), 256, 0, st>>>(boxes1, n1, 5, version == 1, rec1);
-  rec_kernel<<<jdet_ceil_div(n2, 256), 256, 0, st>>>(boxes2, n2, 5, version == 1, rec2);
+  rec_kernel<<<jdet_ceil_div(n1 + n2, 256), 256, 0, st>>>(boxes1, n1, boxes2, n2, version == 1, rec1, rec2, gcount);
   dim3 grid(jdet_ceil_div(n2, kTC), jdet_ceil_div(n1, kTR));
   const bool vec = (n2 % 4 == 0) && (((uintptr_t)ious & 15) == 0);
   const long long pairs = (long long)n1 * n2;
