@@ -305,14 +305,14 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
 // 7x7x2x2) into smem and then does nothing but loads and FMAs: bins are handed to warps through an smem counter
 // (their tap counts differ).  The output slab (SLAB x PH*PW, contiguous in (R,C,PH,PW)) is assembled in smem
 // and leaves as ONE cp.async.bulk store.
-// (256, 4): without a blocks-per-SM hint ptxas squeezes the kernel into 32 registers by sinking every load next
-// to its FMAs; 64 registers keep the 8 loads of a step in flight.
-template <int QL>
-__global__ void __launch_bounds__(256, 4) roi_gather_kernel(const __grid_constant__ RoiLevels L,
+// (256, 4) / (256, 3): without a blocks-per-SM hint ptxas squeezes the kernel into 32 registers by sinking every load
+// next to its FMAs; 64 registers (80 for the two-bins-per-warp form) keep the 8 loads of a step in flight.
+template <int QL, bool PAIR>
+__global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __grid_constant__ RoiLevels L,
                                                              const unsigned char* __restrict__ tables, size_t stride, int C,
                                                              int nbins, int nslabs, int items,
                                                              int* __restrict__ work_counter, float* __restrict__ out) {
-  constexpr int SLAB = 4 * QL;
+  constexpr int SLAB = PAIR ? 8 * QL : 4 * QL;                      // PAIR: a lane owns two channel quads 4*QL apart
   extern __shared__ __align__(128) unsigned char smem[];
   const int S = nbins | 1;                                         // odd row stride of s_out: see the store below
   float* s_out = reinterpret_cast<float*>(smem);                   // [SLAB][S]
@@ -367,6 +367,61 @@ __global__ void __launch_bounds__(256, 4) roi_gather_kernel(const __grid_constan
     const int icnt = (int)count;
     const bool pow2 = (icnt & (icnt - 1)) == 0;                    // x / 2^k == x * 2^-k exactly
     const float rcnt = 1.f / count;
+  if constexpr (PAIR) {
+    // Two bins per warp (one per half-warp of 16 lanes, 8 channels per lane): the per-bin bookkeeping, the table
+    // reads and the address arithmetic of a step are issued once for both bins.  Control flow is uniform across the
+    // warp (steps run to the larger tap count, loads are predicated per lane), 4 taps x 2 quads = 8 loads per step.
+    const int half = lane >> 4;
+    for (;;) {
+      int p = 0;
+      if (lane == 0) p = atomicAdd(&next_bin, 1);
+      p = __shfl_sync(0xffffffffu, p, 0);
+      if (2 * p >= nbins) break;
+      const int bin = 2 * p + half;
+      const bool valid = bin < nbins;
+      const int n = valid ? cnt[bin] : 0;
+      const int nmax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
+      const int2* e = fin + (valid ? bin : 0) * fstride;
+      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+      for (int k = 0; k < nmax; k += 4) {
+        const int4 t01 = *reinterpret_cast<const int4*>(e + k), t23 = *reinterpret_cast<const int4*>(e + k + 2);
+        const float* p0 = base + (size_t)(unsigned)t01.x * (unsigned)C;
+        const float* p1 = base + (size_t)(unsigned)t01.z * (unsigned)C;
+        const float* p2 = base + (size_t)(unsigned)t23.x * (unsigned)C;
+        const float* p3 = base + (size_t)(unsigned)t23.z * (unsigned)C;
+        float4 v[8];
+        v[0] = ldg_v4_if(p0, k + 0 < n); v[1] = ldg_v4_if(p0 + 4 * QL, k + 0 < n);
+        v[2] = ldg_v4_if(p1, k + 1 < n); v[3] = ldg_v4_if(p1 + 4 * QL, k + 1 < n);
+        v[4] = ldg_v4_if(p2, k + 2 < n); v[5] = ldg_v4_if(p2 + 4 * QL, k + 2 < n);
+        v[6] = ldg_v4_if(p3, k + 3 < n); v[7] = ldg_v4_if(p3 + 4 * QL, k + 3 < n);
+#pragma unroll
+        for (int j = 0; j < 8; j++)   // scheduling fence: no FMA may be hoisted between the loads
+          asm volatile("" : "+f"(v[j].x), "+f"(v[j].y), "+f"(v[j].z), "+f"(v[j].w));
+        const float w0 = __int_as_float(t01.y), w1 = __int_as_float(t01.w);   // 0 beyond this bin's tap count
+        const float w2 = __int_as_float(t23.y), w3 = __int_as_float(t23.w);
+        acc0.x += w0 * v[0].x + w1 * v[2].x + w2 * v[4].x + w3 * v[6].x;
+        acc0.y += w0 * v[0].y + w1 * v[2].y + w2 * v[4].y + w3 * v[6].y;
+        acc0.z += w0 * v[0].z + w1 * v[2].z + w2 * v[4].z + w3 * v[6].z;
+        acc0.w += w0 * v[0].w + w1 * v[2].w + w2 * v[4].w + w3 * v[6].w;
+        acc1.x += w0 * v[1].x + w1 * v[3].x + w2 * v[5].x + w3 * v[7].x;
+        acc1.y += w0 * v[1].y + w1 * v[3].y + w2 * v[5].y + w3 * v[7].y;
+        acc1.z += w0 * v[1].z + w1 * v[3].z + w2 * v[5].z + w3 * v[7].z;
+        acc1.w += w0 * v[1].w + w1 * v[3].w + w2 * v[5].w + w3 * v[7].w;
+      }
+      if (valid) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          float4 a = u ? acc1 : acc0;
+          if (pow2) { a.x *= rcnt; a.y *= rcnt; a.z *= rcnt; a.w *= rcnt; }
+          else { a.x /= count; a.y /= count; a.z /= count; a.w /= count; }
+          const float b0 = rot & 1 ? a.y : a.x, b1 = rot & 1 ? a.z : a.y, b2 = rot & 1 ? a.w : a.z, b3 = rot & 1 ? a.x : a.w;
+          const float d0 = rot & 2 ? b2 : b0, d1 = rot & 2 ? b3 : b1, d2 = rot & 2 ? b0 : b2, d3 = rot & 2 ? b1 : b3;
+          float* row = s_out + u * 4 * QL * S + bin;
+          row[ro0] = d0; row[ro1] = d1; row[ro2] = d2; row[ro3] = d3;
+        }
+      }
+    }
+  } else {
   // bins -> warps: round-robin when the bin count is a multiple of the warp count, else handed out through an smem counter
   const bool static_bins = QL == 32 && nbins % (int)(blockDim.x >> 5) == 0;
   for (int sbin = threadIdx.x >> 5;; sbin += blockDim.x >> 5) {
@@ -453,6 +508,7 @@ __global__ void __launch_bounds__(256, 4) roi_gather_kernel(const __grid_constan
       row[ro3] = d3;
     }
   }
+  }   // !PAIR
     // out[r][c0 .. c0+SLAB-1][bins] is one contiguous run of SLAB*nbins floats
     float* dst = out + ((size_t)r * C + c0) * nbins;
     const int total = SLAB * nbins;
@@ -651,16 +707,18 @@ static cudaError_t launch_gather(const RoiLevels& L, const unsigned char* tables
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int threads = 256;   // (7 warps with round-robin bins for 7x7: 124-127 us vs 121 us for 8 warps + smem counter, same box)
-  const int grid = (int)std::min<long long>(items_ll, (long long)sms * 4);
+  const bool pair = slab == 128;   // two bins per warp (A/B on one box, cfg2 whole op: 116.8 vs 122.1 us)
+  const int grid = (int)std::min<long long>(items_ll, (long long)sms * (pair ? 3 : 4));
   // (measured on B200, cfg2, gather only: 16 taps per bin straight from per-CTA tables 106 us; taps merged per bin
   //  95 us; tables moved to the prologue, no other change 90 us; 8 loads per step actually in flight (see the
   //  launch bounds) and lean steps 71 us; persistent CTAs with table prefetch: see profiles/)
-#define JDET_LAUNCH_ROI(QL_)                                                                                           \
+#define JDET_LAUNCH_ROI(QL_, PAIR_)                                                                                    \
   do {                                                                                                                 \
-    if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_gather_kernel<QL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; } \
-    roi_gather_kernel<QL_><<<grid, threads, smem, st>>>(L, tables, stride, C, nbins, nslabs, items, work_counter, output); \
+    if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_gather_kernel<QL_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; } \
+    roi_gather_kernel<QL_, PAIR_><<<grid, threads, smem, st>>>(L, tables, stride, C, nbins, nslabs, items, work_counter, output); \
   } while (0)
-  if (slab == 128) JDET_LAUNCH_ROI(32); else JDET_LAUNCH_ROI(16);
+  if (slab == 128) { if (pair) JDET_LAUNCH_ROI(16, true); else JDET_LAUNCH_ROI(32, false); }
+  else JDET_LAUNCH_ROI(16, false);
 #undef JDET_LAUNCH_ROI
   return cudaGetLastError();
 }
