@@ -188,12 +188,12 @@ def run_ours(args):
     alg_bytes = feat.numel() * 4 + rois.numel() * 4 + out.numel() * 4        # 169 918 464 B
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm",
-                "kernel": "roi_align_rotated = roi_prologue_kernel<1> (re-layout + tap tables) + roi_gather_kernel<32> "
+                "kernel": "roi_align_rotated = roi_prologue_kernel<1> (re-layout + tap tables) + roi_gather_kernel<16, true> "
                           "(2 launches per step; the duration used is the WHOLE step, dominant kernel = the gather, ~69 % of it)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "peak_source": peaks["source"], "algorithmic_bytes": alg_bytes,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels from the committed ncu --set full
-                # capture (profiles/r01_ncu_summary.md, cold L2): prologue 67.2 + 31.8 MB, gather 134.2 + 73.4 MB
+                # capture (profiles/r01_ncu_summary.md, cold L2): prologue 67.2 + 31.8 MB, gather 134.9 + 73.4 MB
                 "traffic": 306_600_000,
                 "note": "the gather is bound by the SM's L1 data path and issue slots (l1tex 57 %, issue 60 %, no DRAM/L2 "
                         "limit in sight: an L2-resident random 1-KB gather probe reaches 19-20 TB/s on this GPU, "
