@@ -91,6 +91,17 @@ def lib():
     """ctypes handle with argtypes set.  Raises (never falls back) if the library is missing."""
     global _lib
     if _lib is None:
+        alt = os.environ.get("JDET_B200_LIB")      # a prebuilt library elsewhere (A/B timing of two builds: tools/ab_libs.py)
+        if alt:
+            if not os.path.exists(alt):
+                raise RuntimeError("JDET_B200_LIB=%s does not exist" % alt)
+            L = ctypes.CDLL(alt)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+            return _lib
         if _stale():
             try:
                 build()

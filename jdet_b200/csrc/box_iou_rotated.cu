@@ -26,6 +26,10 @@
 namespace jdet {
 
 constexpr int kTR = 64, kTC = 128, kThreads = 256;
+#ifndef JDET_IOU_TILE_MINB
+#define JDET_IOU_TILE_MINB 6          // resident CTAs per SM asked of ptxas (<= 42 registers)
+#endif
+constexpr int kQCap = 2048;        // survivor queue entries per round (a 64 x 128 tile holds 8192 pairs)
 
 // tag handling: IoU has no labels; tag = 1.0f marks a forced-zero box (v1 small-box post pass).
 // both box sets in one launch (small problems are launch-bound); also resets the candidate counter
@@ -46,16 +50,16 @@ __global__ void __launch_bounds__(256) rec_kernel(const float* __restrict__ boxe
 }
 
 template <int VERSION, bool VEC4>
-__global__ void __launch_bounds__(kThreads) iou_tile_kernel(const BoxRec* __restrict__ rec1, int n1,
+__global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(const BoxRec* __restrict__ rec1, int n1,
                                                              const BoxRec* __restrict__ rec2, int n2,
                                                              float* __restrict__ out, int* __restrict__ gcount,
                                                              uint2* __restrict__ gqueue, int gcap, int variant) {
   __shared__ BoxRec s_row[kTR];
   __shared__ BoxRec s_col[kTC];
   __shared__ __align__(16) float s_cx[kTC], s_cy[kTC], s_cr[kTC];
-  __shared__ unsigned short s_q1[kTR * kTC];
-  __shared__ unsigned short s_q2[kTR * kTC];
-  __shared__ int s_cnt1, s_cnt2;
+  __shared__ unsigned short s_q1[kQCap];
+  __shared__ unsigned short s_q2[kQCap];
+  __shared__ int s_cnt1, s_cnt2, s_base;
 
   const int tid = threadIdx.x;
   const int row0 = blockIdx.y * kTR, col0 = blockIdx.x * kTC;
@@ -107,71 +111,78 @@ __global__ void __launch_bounds__(kThreads) iou_tile_kernel(const BoxRec* __rest
       }
     }
   }
-  // compact survivors: warp exclusive scan of popcounts, one atomic per warp
-  {
-    const int cnt = __popc(surv);
-    int incl = cnt;
+  // Survivors -> SAT -> device-wide queue, in rounds of at most kQCap queued survivors (a tile normally has a few
+  // hundred; the small queues keep 8 CTAs resident per SM, which is what hides the load -> store -> atomic latency
+  // chain of these short CTAs).  Whatever does not fit stays in the per-thread masks for the next round.
+  for (;;) {
+    {  // compact: warp exclusive scan of popcounts, one atomic per warp
+      const int cnt = __popc(surv);
+      int incl = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int base = 0;
+      if (lane == 31 && total > 0) base = atomicAdd(&s_cnt1, total);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      int pos = base + incl - cnt;
+      while (surv && pos < kQCap) {
+        const int b = __ffs(surv) - 1;
+        surv &= surv - 1;
+        const int r = warp * 8 + (b >> 2), c = 4 * lane + (b & 3);
+        s_q1[pos++] = (unsigned short)((r << 7) | c);
+      }
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(&s_cnt1, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    int pos = base + incl - cnt;
-    while (surv) {
-      const int b = __ffs(surv) - 1;
-      surv &= surv - 1;
-      const int r = warp * 8 + (b >> 2), c = 4 * lane + (b & 3);
-      s_q1[pos++] = (unsigned short)((r << 7) | c);
-    }
-  }
-  __syncthreads();
+    const int pending = __syncthreads_or(surv != 0u);
 
-  // ---- phase 2: SAT on circle survivors ------------------------------------------------------
-  const int cnt1 = s_cnt1;
-  for (int base = 0; base < cnt1; base += kThreads) {
-    const int k = base + tid;
-    bool keep = false;
-    unsigned short e = 0;
-    if (k < cnt1) {
-      e = s_q1[k];
-      keep = !sat_disjoint<VERSION>(s_row[e >> 7], s_col[e & 127]);
+    // ---- phase 2: SAT on circle survivors ----------------------------------------------------
+    const int cnt1 = min(s_cnt1, kQCap);
+    for (int base = 0; base < cnt1; base += kThreads) {
+      const int k = base + tid;
+      bool keep = false;
+      unsigned short e = 0;
+      if (k < cnt1) {
+        e = s_q1[k];
+        keep = !sat_disjoint<VERSION>(s_row[e >> 7], s_col[e & 127]);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (bal) {
+        int wbase = 0;
+        if (lane == 0) wbase = atomicAdd(&s_cnt2, __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (keep) s_q2[wbase + __popc(bal & ((1u << lane) - 1u))] = e;
+      }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (bal) {
-      int wbase = 0;
-      if (lane == 0) wbase = atomicAdd(&s_cnt2, __popc(bal));
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (keep) s_q2[wbase + __popc(bal & ((1u << lane) - 1u))] = e;
-    }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- hand-off: candidates go to the device-wide queue drained by iou_exact_kernel (every lane of
-  // every warp busy there, no barriers); if the queue is full this CTA evaluates its own candidates.
-  const int cnt2 = s_cnt2;
-  __shared__ int s_base;
-  if (tid == 0) s_base = cnt2 > 0 ? atomicAdd(gcount, cnt2) : 0;
-  __syncthreads();
-  const int gbase = s_base;
-  if (gbase + cnt2 <= gcap) {
-    for (int k = tid; k < cnt2; k += kThreads) {
-      const unsigned short e = s_q2[k];
-      gqueue[gbase + k] = make_uint2((unsigned)(row0 + (e >> 7)), (unsigned)(col0 + (e & 127)));
+    // ---- hand-off: candidates go to the device-wide queue drained by iou_exact_kernel (every lane of
+    // every warp busy there, no barriers); if the queue is full this CTA evaluates its own candidates.
+    const int cnt2 = s_cnt2;
+    if (tid == 0) s_base = cnt2 > 0 ? atomicAdd(gcount, cnt2) : 0;
+    __syncthreads();
+    const int gbase = s_base;
+    if (gbase + cnt2 <= gcap) {
+      for (int k = tid; k < cnt2; k += kThreads) {
+        const unsigned short e = s_q2[k];
+        gqueue[gbase + k] = make_uint2((unsigned)(row0 + (e >> 7)), (unsigned)(col0 + (e & 127)));
+      }
+    } else {
+      for (int k = tid; k < cnt2; k += kThreads) {
+        if (gbase + k < gcap) gqueue[gbase + k] = make_uint2(0xffffffffu, 0u);   // reserved but unused slot
+        const unsigned short e = s_q2[k];
+        const int r = e >> 7, c = e & 127;
+        const BoxRec& A = s_row[r];
+        const BoxRec& B = s_col[c];
+        out[(size_t)(row0 + r) * n2 + (col0 + c)] =
+            (A.tag == 0.f && B.tag == 0.f) ? (variant ? iou_exact<VERSION, 1>(A, B) : iou_exact<VERSION, 0>(A, B)) : 0.f;
+      }
     }
-  } else {
-    for (int k = tid; k < cnt2; k += kThreads) {
-      if (gbase + k < gcap) gqueue[gbase + k] = make_uint2(0xffffffffu, 0u);   // reserved but unused slot
-      const unsigned short e = s_q2[k];
-      const int r = e >> 7, c = e & 127;
-      const BoxRec& A = s_row[r];
-      const BoxRec& B = s_col[c];
-      out[(size_t)(row0 + r) * n2 + (col0 + c)] =
-          (A.tag == 0.f && B.tag == 0.f) ? (variant ? iou_exact<VERSION, 1>(A, B) : iou_exact<VERSION, 0>(A, B)) : 0.f;
-    }
+    if (!pending) break;
+    __syncthreads();
+    if (tid == 0) { s_cnt1 = 0; s_cnt2 = 0; }
+    __syncthreads();
   }
 }
 
