@@ -27,7 +27,7 @@ namespace jdet {
 
 constexpr int kTR = 64, kTC = 128, kThreads = 256;
 #ifndef JDET_IOU_TILE_MINB
-#define JDET_IOU_TILE_MINB 6          // resident CTAs per SM asked of ptxas (<= 42 registers)
+#define JDET_IOU_TILE_MINB 8          // resident CTAs per SM asked of ptxas (32 registers; A/B on one B200, 16k x 16k: 4 -> 537 us, 6 -> 525, 8 -> 517)
 #endif
 constexpr int kQCap = 2048;        // survivor queue entries per round (a 64 x 128 tile holds 8192 pairs)
 
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
   __shared__ BoxRec s_row[kTR];
   __shared__ BoxRec s_col[kTC];
   __shared__ __align__(16) float s_cx[kTC], s_cy[kTC], s_cr[kTC];
+  __shared__ float4 s_rq[kTR];                          // rows: (x, y, qr, -) for the broadcast loads of phase 1
   __shared__ unsigned short s_q1[kQCap];
   __shared__ unsigned short s_q2[kQCap];
   __shared__ int s_cnt1, s_cnt2, s_base;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
     } else {
       r.x = r.y = r.w = r.h = r.c2 = r.s2 = 0.f; r.qr = -INFINITY; r.tag = 1.f;
     }
-    if (is_row) s_row[tid] = r;
+    if (is_row) { s_row[tid] = r; s_rq[tid] = make_float4(r.x, r.y, r.qr, 0.f); }
     else {
       const int c = tid - kTR;
       s_col[c] = r; s_cx[c] = r.x; s_cy[c] = r.y; s_cr[c] = r.qr;
@@ -84,33 +85,38 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
   __syncthreads();
 
   // ---- phase 1: circle test over the whole tile, zero stores ---------------------------------
+  // 8 issue slots per pair is what this kernel runs out of (ncu: 79 % SM busy at 4.5 TB/s of stores), so the test
+  // is 6 float ops whose SIGN is the verdict, shifted into the per-thread mask by one funnel shift — no compare,
+  // select or OR per pair — and a row costs one broadcast LDS.128, one pointer add and one 16-B store.
   const int warp = tid >> 5, lane = tid & 31;
   const float4 cx = reinterpret_cast<const float4*>(s_cx)[lane];
   const float4 cy = reinterpret_cast<const float4*>(s_cy)[lane];
   const float4 cr = reinterpret_cast<const float4*>(s_cr)[lane];
-  unsigned surv = 0;
+  unsigned rej = 0;                                     // pair p = 4 * k + q ends up in bit 31 - p
+  {
+    const int gc = col0 + 4 * lane;
+    float* o = out + (size_t)(row0 + warp * 8) * n2 + gc;
+    const int rows_left = n1 - (row0 + warp * 8);
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int r = warp * 8 + k;
-    const float rx = s_row[r].x, ry = s_row[r].y, rr = s_row[r].qr;
-    unsigned m = 0;
-    m |= circle_disjoint(rx, ry, rr, cx.x, cy.x, cr.x) ? 0u : 1u;
-    m |= circle_disjoint(rx, ry, rr, cx.y, cy.y, cr.y) ? 0u : 2u;
-    m |= circle_disjoint(rx, ry, rr, cx.z, cy.z, cr.z) ? 0u : 4u;
-    m |= circle_disjoint(rx, ry, rr, cx.w, cy.w, cr.w) ? 0u : 8u;
-    surv |= m << (4 * k);
-    const int gr = row0 + r, gc = col0 + 4 * lane;
-    if (gr < n1) {
-      float* o = out + (size_t)gr * n2 + gc;
-      if (VEC4) {
-        if (gc < n2) st_stream_v4(o, 0.f, 0.f, 0.f, 0.f);   // n2 % 4 == 0 => all four in range
-      } else {
+    for (int k = 0; k < 8; k++) {
+      const float4 rq = s_rq[warp * 8 + k];
+      rej = circle_reject_shift(rej, rq.x, rq.y, rq.z, cx.x, cy.x, cr.x);
+      rej = circle_reject_shift(rej, rq.x, rq.y, rq.z, cx.y, cy.y, cr.y);
+      rej = circle_reject_shift(rej, rq.x, rq.y, rq.z, cx.z, cy.z, cr.z);
+      rej = circle_reject_shift(rej, rq.x, rq.y, rq.z, cx.w, cy.w, cr.w);
+      if (k < rows_left) {
+        if (VEC4) {
+          if (gc < n2) st_stream_v4(o, 0.f, 0.f, 0.f, 0.f);   // n2 % 4 == 0 => all four in range
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (gc + q < n2) st_stream(o + q, 0.f);
+          for (int q = 0; q < 4; q++)
+            if (gc + q < n2) st_stream(o + q, 0.f);
+        }
       }
+      o += n2;
     }
   }
+  unsigned surv = __brev(~rej);                         // bit p: pair (row warp * 8 + p / 4, column 4 * lane + p % 4) survives
   // Survivors -> SAT -> device-wide queue, in rounds of at most kQCap queued survivors (a tile normally has a few
   // hundred; the small queues keep 8 CTAs resident per SM, which is what hides the load -> store -> atomic latency
   // chain of these short CTAs).  Whatever does not fit stays in the per-thread masks for the next round.
@@ -175,8 +181,8 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
         const int r = e >> 7, c = e & 127;
         const BoxRec& A = s_row[r];
         const BoxRec& B = s_col[c];
-        out[(size_t)(row0 + r) * n2 + (col0 + c)] =
-            (A.tag == 0.f && B.tag == 0.f) ? (variant ? iou_exact<VERSION, 1>(A, B) : iou_exact<VERSION, 0>(A, B)) : 0.f;
+        out[(size_t)(row0 + r) * n2 + (col0 + c)] =   // (rare path: the compact routine, for this kernel's register count)
+            (A.tag == 0.f && B.tag == 0.f) ? (variant ? iou_exact_general<VERSION, 1>(A, B) : iou_exact_general<VERSION, 0>(A, B)) : 0.f;
       }
     }
     if (!pending) break;
@@ -186,19 +192,24 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
   }
 }
 
-// Exact IoU for the queued candidates: one thread per pair, grid-stride over the device-side count.
+// Exact IoU for the queued candidates: one thread per pair, grid-stride over the device-side count.  The clip points of
+// a pair live in a [slot][thread] shared-memory array (48 KB per CTA, 4 CTAs per SM), see iou_exact_shared.
+constexpr int kExactThreads = 256;
+constexpr size_t kExactSmem = (size_t)3 * kExactCap * kExactThreads * sizeof(float);
 template <int VERSION>
-__global__ void __launch_bounds__(256) iou_exact_kernel(const BoxRec* __restrict__ rec1, const BoxRec* __restrict__ rec2,
+__global__ void __launch_bounds__(kExactThreads) iou_exact_kernel(const BoxRec* __restrict__ rec1, const BoxRec* __restrict__ rec2,
                                                          int n2, const int* __restrict__ gcount,
                                                          const uint2* __restrict__ gqueue, int gcap,
                                                          float* __restrict__ out, int variant) {
+  extern __shared__ float s_pts[];
+  float* sq = s_pts + threadIdx.x;
   const int total = min(*gcount, gcap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint2 e = gqueue[i];
     if (e.x == 0xffffffffu) continue;
     const BoxRec A = rec1[e.x], B = rec2[e.y];
     out[(size_t)e.x * n2 + e.y] =
-        (A.tag == 0.f && B.tag == 0.f) ? (variant ? iou_exact<VERSION, 1>(A, B) : iou_exact<VERSION, 0>(A, B)) : 0.f;
+        (A.tag == 0.f && B.tag == 0.f) ? (variant ? iou_exact_shared<VERSION, kExactThreads>(A, B, sq) : iou_exact<VERSION, 0>(A, B)) : 0.f;
   }
 }
 
@@ -253,14 +264,16 @@ JDET_API int jdet_box_iou_rotated_ex(const float* boxes1, int n1, const float* b
   const bool vec = (n2 % 4 == 0) && (((uintptr_t)ious & 15) == 0);
   const long long pairs = (long long)n1 * n2;
   const int xgrid = (int)(pairs < 256 * 1024 ? (pairs + 255) / 256 : kNumSMs * 8);
+  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(iou_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExactSmem));
+  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(iou_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExactSmem));
   if (version == 0) {
     if (vec) iou_tile_kernel<0, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
     else     iou_tile_kernel<0, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
-    iou_exact_kernel<0><<<xgrid, 256, 0, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious, variant);
+    iou_exact_kernel<0><<<xgrid, kExactThreads, kExactSmem, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious, variant);
   } else {
     if (vec) iou_tile_kernel<1, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
     else     iou_tile_kernel<1, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
-    iou_exact_kernel<1><<<xgrid, 256, 0, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious, variant);
+    iou_exact_kernel<1><<<xgrid, kExactThreads, kExactSmem, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious, variant);
   }
   return (int)cudaGetLastError();
 }

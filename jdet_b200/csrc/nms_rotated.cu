@@ -141,7 +141,7 @@ __device__ __forceinline__ long long tri_index(long long rb, long long cb) { ret
 //   phase 1  thread <-> 2 columns (registers), loop over the 64 rows (broadcast LDS.128): circle test
 //   phase 2  SAT on compacted survivors          phase 3  exact IoU, strict "> thr", bits via smem atomics
 // label_in_pair != 0 (thr < 0 corner): single segment, no quick rejects, label mismatch => IoU 0.
-__global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
+__global__ void __launch_bounds__(kMaskThreads, 3) nms_mask_kernel(
     const BoxRec* __restrict__ rec, const int* __restrict__ seg_start, const int* __restrict__ item_base,
     const long long* __restrict__ tile_base, const int* __restrict__ scan, int n, float thr,
     int flags, int* __restrict__ counter, unsigned long long* __restrict__ mask,
@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
     // ---- phase 1 ---------------------------------------------------------------------------------
     unsigned long long m[kColsPerThread];                 // bit r: (row r, my column j) survives
     if (!label_in_pair) {
-      unsigned wlo[kColsPerThread], whi[kColsPerThread];  // constant shifts after unrolling
+      // the verdict of a circle test is the SIGN of R|R| - d^2, shifted into the word by one funnel shift (row r lands
+      // in bit 31 - r; one bit reversal per word at the end): 7 issue slots per pair, no compare / select / OR
+      unsigned wlo[kColsPerThread], whi[kColsPerThread];
 #pragma unroll
       for (int j = 0; j < kColsPerThread; j++) { wlo[j] = 0u; whi[j] = 0u; }
 #pragma unroll
@@ -217,12 +219,12 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
         const float4 ra = s_rowq[r], rb2 = s_rowq[r + 32];
 #pragma unroll
         for (int j = 0; j < kColsPerThread; j++) {
-          wlo[j] |= (circle_disjoint(ra.x, ra.y, ra.z, cx[j], cy[j], cq[j]) ? 0u : 1u) << r;
-          whi[j] |= (circle_disjoint(rb2.x, rb2.y, rb2.z, cx[j], cy[j], cq[j]) ? 0u : 1u) << r;
+          wlo[j] = circle_reject_shift(wlo[j], ra.x, ra.y, ra.z, cx[j], cy[j], cq[j]);
+          whi[j] = circle_reject_shift(whi[j], rb2.x, rb2.y, rb2.z, cx[j], cy[j], cq[j]);
         }
       }
 #pragma unroll
-      for (int j = 0; j < kColsPerThread; j++) m[j] = ((unsigned long long)whi[j] << 32) | wlo[j];
+      for (int j = 0; j < kColsPerThread; j++) m[j] = ((unsigned long long)__brev(~whi[j]) << 32) | __brev(~wlo[j]);
     } else {
       const int nrow = min(64, cnt - rb * 64);
       const unsigned long long rows = nrow >= 64 ? ~0ull : ((1ull << nrow) - 1ull);
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(kMaskThreads) nms_mask_kernel(
           const BoxRec& B = s_col[tt * 64 + cc];
           float v;
           if (label_in_pair && A.tag != B.tag) v = 0.f;   // nms_rotated.py:285-286
-          else v = cpu_arith ? iou_exact<0, 0>(A, B) : iou_exact<0, 1>(A, B);
+          else v = cpu_arith ? iou_exact_general<0, 0>(A, B) : iou_exact_general<0, 1>(A, B);   // (rare path: the compact routine keeps this kernel's register count down)
           if (v > thr) atomicOr(&s_bits[(tt * 64 + r) * 2 + (cc >> 5)], 1u << (cc & 31));
         }
       }
@@ -338,6 +340,8 @@ __global__ void __launch_bounds__(256) nms_exact_kernel(const BoxRec* __restrict
                                                          int flags, unsigned long long* __restrict__ mask) {
   const int label_in_pair = flags & 1;
   const bool cpu_arith = (flags & 2) != 0;
+  extern __shared__ float s_pts[];                     // clip points, [slot][thread]: see iou_exact_shared
+  float* sq = s_pts + threadIdx.x;
   const int total = min(counter[1], xcap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint4 e = xqueue[i];
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(256) nms_exact_kernel(const BoxRec* __restrict
     const BoxRec A = rec[e.x], B = rec[e.y];
     float v;
     if (label_in_pair && A.tag != B.tag) v = 0.f;
-    else v = cpu_arith ? iou_exact<0, 0>(A, B) : iou_exact<0, 1>(A, B);
+    else v = cpu_arith ? iou_exact<0, 0>(A, B) : iou_exact_shared<0, 256>(A, B, sq);
     if (v > thr) {
       const unsigned long long word = ((unsigned long long)(e.w >> 8) << 32) | e.z;
       atomicOr(mask + word, 1ull << (e.w & 63u));
@@ -517,7 +521,9 @@ JDET_API int jdet_nms_rotated_ex(const float* dets, int n, int box_length, const
   nms_mask_kernel<<<kNumSMs * 3, kMaskThreads, mask_smem, st>>>(w.rec, w.seg_start, w.item_base, w.tile_base,
                                                         w.flag_scan, n, iou_threshold, flags,
                                                         w.counters, w.mask, w.xqueue, w.xcap);
-  nms_exact_kernel<<<kNumSMs * 8, 256, 0, st>>>(w.rec, w.counters, w.xqueue, w.xcap, iou_threshold, flags, w.mask);
+  const size_t exact_smem = (size_t)3 * kExactCap * 256 * sizeof(float);
+  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem));
+  nms_exact_kernel<<<kNumSMs * 8, 256, exact_smem, st>>>(w.rec, w.counters, w.xqueue, w.xcap, iou_threshold, flags, w.mask);
   const size_t smem = (size_t)jdet_ceil_div(n, 64) * 8;
   if (smem > 48 * 1024)
     JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -17,10 +17,19 @@ static float pair(const BoxRec& A, const BoxRec& B, int mode, int* counts) {
   }
   if (!(A.tag == 0.f && B.tag == 0.f)) return 0.f;
   counts[2]++;
+  if (mode == 3) {   // strided point store with few slots (the exact kernels' shared-memory form): overflow must fall back
+    float buf[3 * 4 * 6];
+    return iou_exact_core<VERSION, 1, 4, 6>(A, B, buf, buf + 4 * 6, buf + 2 * 4 * 6);
+  }
+  if (mode == 4) {   // the kernels' own capacity
+    float buf[3 * 2 * kExactCap];
+    return iou_exact_core<VERSION, 1, 2, kExactCap>(A, B, buf, buf + 2 * kExactCap, buf + 4 * kExactCap);
+  }
   return mode == 0 ? iou_exact_general<VERSION, VARIANT>(A, B) : iou_exact<VERSION, VARIANT>(A, B);
 }
 
-// mode 0: iou_exact_general for every pair; 1: iou_exact (fast path + fallback) for every pair; 2: full stage pipeline
+// mode 0: iou_exact_general for every pair; 1: iou_exact (fast path + fallback) for every pair; 2: full stage pipeline;
+// 3 / 4: the strided, capacity-limited point store of the exact kernels (CUDA-build arithmetic only)
 extern "C" void host_geom_iou(const float* b1, int n1, const float* b2, int n2, float* out, int version, int variant,
                               int mode, int* counts) {
   BoxRec* r1 = new BoxRec[n1 > 0 ? n1 : 1];
