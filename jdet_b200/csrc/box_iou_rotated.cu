@@ -29,7 +29,10 @@ constexpr int kTR = 64, kTC = 128, kThreads = 256;
 #ifndef JDET_IOU_TILE_MINB
 #define JDET_IOU_TILE_MINB 8          // resident CTAs per SM asked of ptxas (32 registers; A/B on one B200, 16k x 16k: 4 -> 537 us, 6 -> 525, 8 -> 517)
 #endif
-constexpr int kQCap = 2048;        // survivor queue entries per round (a 64 x 128 tile holds 8192 pairs)
+#ifndef JDET_IOU_QCAP
+#define JDET_IOU_QCAP 2048
+#endif
+constexpr int kQCap = JDET_IOU_QCAP;        // survivor queue entries per round (a 64 x 128 tile holds 8192 pairs)
 
 // tag handling: IoU has no labels; tag = 1.0f marks a forced-zero box (v1 small-box post pass).
 // both box sets in one launch (small problems are launch-bound); also resets the candidate counter

@@ -51,6 +51,17 @@ __device__ __forceinline__ float4 ldg_v4_if(const float* p, bool live) {
   return v;
 }
 
+// 16-B read-only load into v when live; v keeps its value otherwise (no zero-fill: the caller owns the initial state).
+// volatile for the same reason as above.
+__device__ __forceinline__ void ldg_v4_keep(float4& v, const float* p, bool live) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.s32 q, %5, 0;\n\t"
+      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "l"(p), "r"((int)live));
+}
+
 // ---- mbarrier / bulk-async-copy helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

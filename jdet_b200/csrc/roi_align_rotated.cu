@@ -122,9 +122,11 @@ void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cuda
 // Ends with a barrier; raw may be reused afterwards.
 template <int VERSION>
 __device__ __forceinline__ void build_tap_table(const RoiGeom& g, int nbins, int PW, int H, int W, int2* raw, int2* fin,
-                                                int fstride, int* cnt) {
-  // fin holds fstride >= tpb (a multiple of 8) entries per bin: cnt[bin] merged taps, then (0, 0.f) entries, so a
-  // reader may run 8-wide steps whose tail needs a load predicate but no weight select.
+                                                int fstride, int* cnt, unsigned scale = 1u) {
+  // fin holds fstride >= tpb (a multiple of 8) entries per bin: cnt[bin] merged taps (pixel index * scale, weight),
+  // then padding entries (the bin's LAST pixel again, weight 0.f; (0, 0.f) for a bin without taps): a reader may run
+  // fixed-width steps over the padding with plain loads — they hit the line the previous tap just fetched and add
+  // 0 * value — or predicate them off by count.
   const int spb = g.gh * g.gw, tpb = 4 * spb;
   for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
     const int bin = s / spb, k = s - bin * spb;
@@ -152,10 +154,12 @@ __device__ __forceinline__ void build_tap_table(const RoiGeom& g, int nbins, int
       const unsigned lb = __ballot_sync(0xffffffffu, leader) & gm;
       const int nlead = __popc(lb);
       const int pos = leader ? __popc(lb & below) : nlead + __popc(~lb & gm & below);
+      const int last = __shfl_sync(0xffffffffu, me.x, lb ? 31 - __clz(lb) : 0);       // pixel of the bin's last merged tap
+      const int2 pad = make_int2(nlead ? (int)((unsigned)last * scale) : 0, 0);
       if (in) {
         int2* fb = fin + bin * fstride;
-        fb[pos] = leader ? make_int2(me.x, __float_as_int(wsum)) : make_int2(0, 0);
-        for (int i = tpb + sl; i < fstride; i += tpb) fb[i] = make_int2(0, 0);
+        fb[pos] = leader ? make_int2((int)((unsigned)me.x * scale), __float_as_int(wsum)) : pad;
+        for (int i = tpb + sl; i < fstride; i += tpb) fb[i] = pad;
         if (sl == 0) cnt[bin] = nlead;
       }
     }
@@ -163,12 +167,13 @@ __device__ __forceinline__ void build_tap_table(const RoiGeom& g, int nbins, int
     for (int bin = threadIdx.x; bin < nbins; bin += blockDim.x) {
       int2* fb = fin + bin * fstride;
       int n = 0;
+      int2 pad = make_int2(0, 0);
       for (int j = 0; j < tpb; j++) {
         const int2 e = raw[bin * tpb + j];
-        if (e.x >= 0) fb[n++] = e;
+        if (e.x >= 0) { pad = make_int2((int)((unsigned)e.x * scale), 0); fb[n++] = make_int2(pad.x, e.y); }
       }
       cnt[bin] = n;
-      for (; n < fstride; n++) fb[n] = make_int2(0, 0);
+      for (; n < fstride; n++) fb[n] = pad;
     }
   }
   __syncthreads();
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
   int2* fin = reinterpret_cast<int2*>(cnt + ((nbins + 3) & ~3));
   int2* raw = fin + nbins * fstride;
   if (threadIdx.x == 0) *hdr = make_int4(g.batch, __float_as_int(g.inv_count), fstride, level);
-  build_tap_table<VERSION>(g, nbins, PW, L.lv[level].H, L.lv[level].W, raw, fin, fstride, cnt);
+  build_tap_table<VERSION>(g, nbins, PW, L.lv[level].H, L.lv[level].W, raw, fin, fstride, cnt, 4u * (unsigned)C);   // entries: BYTE offsets into one image of the channel-last map
   const size_t stride = roi_table_stride(nbins, sample_num);
   int4* dst = reinterpret_cast<int4*>(tables + (size_t)idx * stride);
   for (int i = threadIdx.x; i < (int)(stride / 16); i += blockDim.x) dst[i] = hdr[i];
@@ -383,30 +388,33 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
       const int nmax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
       const int2* e = fin + (valid ? bin : 0) * fstride;
       float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+      // A step = 4 table entries x 2 channel quads = 8 loads, all issued before the first FMA.  Entries past this
+      // bin's count are padding (its last pixel again, weight 0): plain loads that hit the line just fetched, so a
+      // step carries no per-tap predicates or zero-fills; only a bin without any tap (n == 0, paired with a live
+      // one) keeps its loads switched off, and its registers stay at the zeros set here.
+      const bool live = n > 0;
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = 0; k < nmax; k += 4) {
         const int4 t01 = *reinterpret_cast<const int4*>(e + k), t23 = *reinterpret_cast<const int4*>(e + k + 2);
-        const float* p0 = base + (size_t)(unsigned)t01.x * (unsigned)C;
-        const float* p1 = base + (size_t)(unsigned)t01.z * (unsigned)C;
-        const float* p2 = base + (size_t)(unsigned)t23.x * (unsigned)C;
-        const float* p3 = base + (size_t)(unsigned)t23.z * (unsigned)C;
-        float4 v[8];
-        v[0] = ldg_v4_if(p0, k + 0 < n); v[1] = ldg_v4_if(p0 + 4 * QL, k + 0 < n);
-        v[2] = ldg_v4_if(p1, k + 1 < n); v[3] = ldg_v4_if(p1 + 4 * QL, k + 1 < n);
-        v[4] = ldg_v4_if(p2, k + 2 < n); v[5] = ldg_v4_if(p2 + 4 * QL, k + 2 < n);
-        v[6] = ldg_v4_if(p3, k + 3 < n); v[7] = ldg_v4_if(p3 + 4 * QL, k + 3 < n);
+        const float* p0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (unsigned)t01.x);
+        const float* p1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (unsigned)t01.z);
+        const float* p2 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (unsigned)t23.x);
+        const float* p3 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (unsigned)t23.z);
+        ldg_v4_keep(v[0], p0, live); ldg_v4_keep(v[1], p0 + 4 * QL, live);
+        ldg_v4_keep(v[2], p1, live); ldg_v4_keep(v[3], p1 + 4 * QL, live);
+        ldg_v4_keep(v[4], p2, live); ldg_v4_keep(v[5], p2 + 4 * QL, live);
+        ldg_v4_keep(v[6], p3, live); ldg_v4_keep(v[7], p3 + 4 * QL, live);
 #pragma unroll
         for (int j = 0; j < 8; j++)   // scheduling fence: no FMA may be hoisted between the loads
           asm volatile("" : "+f"(v[j].x), "+f"(v[j].y), "+f"(v[j].z), "+f"(v[j].w));
-        const float w0 = __int_as_float(t01.y), w1 = __int_as_float(t01.w);   // 0 beyond this bin's tap count
+        const float w0 = __int_as_float(t01.y), w1 = __int_as_float(t01.w);   // 0 on padding
         const float w2 = __int_as_float(t23.y), w3 = __int_as_float(t23.w);
-        acc0.x += w0 * v[0].x + w1 * v[2].x + w2 * v[4].x + w3 * v[6].x;
-        acc0.y += w0 * v[0].y + w1 * v[2].y + w2 * v[4].y + w3 * v[6].y;
-        acc0.z += w0 * v[0].z + w1 * v[2].z + w2 * v[4].z + w3 * v[6].z;
-        acc0.w += w0 * v[0].w + w1 * v[2].w + w2 * v[4].w + w3 * v[6].w;
-        acc1.x += w0 * v[1].x + w1 * v[3].x + w2 * v[5].x + w3 * v[7].x;
-        acc1.y += w0 * v[1].y + w1 * v[3].y + w2 * v[5].y + w3 * v[7].y;
-        acc1.z += w0 * v[1].z + w1 * v[3].z + w2 * v[5].z + w3 * v[7].z;
-        acc1.w += w0 * v[1].w + w1 * v[3].w + w2 * v[5].w + w3 * v[7].w;
+#define JDET_ACC(a, c, i0) a.c = fmaf(w3, v[i0 + 6].c, fmaf(w2, v[i0 + 4].c, fmaf(w1, v[i0 + 2].c, fmaf(w0, v[i0].c, a.c))))
+        JDET_ACC(acc0, x, 0); JDET_ACC(acc0, y, 0); JDET_ACC(acc0, z, 0); JDET_ACC(acc0, w, 0);
+        JDET_ACC(acc1, x, 1); JDET_ACC(acc1, y, 1); JDET_ACC(acc1, z, 1); JDET_ACC(acc1, w, 1);
+#undef JDET_ACC
       }
       if (valid) {
 #pragma unroll
@@ -439,7 +447,7 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
     // is one more step of (4 plain +) up to 3 predicated loads — never dummy loads: every 512-B tap costs ~8
     // cycles of the SM's L1 data path whether it hits or not, and that path and the issue slots, not HBM or L2,
     // are what this kernel runs out of.
-#define JDET_TAP_ADDR(j) (base + (size_t)(unsigned)t[j].x * (unsigned)C)
+#define JDET_TAP_ADDR(j) reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (unsigned)t[j].x)
 #define JDET_TAP_FMA(j)                                                                                                \
   do {                                                                                                                 \
     const float w_ = __int_as_float(t[j].y);                                                                           \
@@ -677,6 +685,8 @@ static cudaError_t launch_prologue(int version, const float* input_nchw, float* 
   const int nbins = PH * PW;
   const size_t stride = roi_table_stride(nbins, sampling_ratio);
   const int Rt = with_tables ? R : 0;
+  for (int l = 0; l < L.n; l++)   // table entries are 32-bit byte offsets into one image of the channel-last map
+    if ((unsigned long long)L.lv[l].H * L.lv[l].W * C >= (1ull << 30)) return cudaErrorInvalidConfiguration;
   const bool vec = input_nchw && ((H * W) & 3) == 0 && (C & 3) == 0 && ((((uintptr_t)input_nchw) | ((uintptr_t)nhwc_scratch)) & 15) == 0;
   const int tiles_x = input_nchw ? jdet_ceil_div(H * W, vec ? kTileW : 32) : 0, tiles_y = input_nchw ? jdet_ceil_div(C, 32) : 0;
   const int rows = input_nchw ? tiles_y * B : jdet_ceil_div(Rt, 1024);
