@@ -30,7 +30,7 @@ constexpr int kTR = 64, kTC = 128, kThreads = 256;
 #define JDET_IOU_TILE_MINB 8          // resident CTAs per SM asked of ptxas (32 registers; A/B on one B200, 16k x 16k: 4 -> 537 us, 6 -> 525, 8 -> 517)
 #endif
 #ifndef JDET_IOU_QCAP
-#define JDET_IOU_QCAP 2048
+#define JDET_IOU_QCAP 4096          // (clustered 4k x 4k on one B200: 1024 -> 134 us, 2048 -> 128, 4096 -> 118; 16k x 16k DOTA-shaped: no difference)
 #endif
 constexpr int kQCap = JDET_IOU_QCAP;        // survivor queue entries per round (a 64 x 128 tile holds 8192 pairs)
 

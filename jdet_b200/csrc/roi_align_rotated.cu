@@ -716,8 +716,11 @@ static cudaError_t launch_gather(const RoiLevels& L, const unsigned char* tables
   const int items = (int)items_ll;
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int threads = 256;   // (7 warps with round-robin bins for 7x7: 124-127 us vs 121 us for 8 warps + smem counter, same box)
   const bool pair = slab == 128;   // two bins per warp (A/B on one box, cfg2 whole op: 116.8 vs 122.1 us)
+  // (warps per CTA, pair mode, 7x7 = 25 warp-tasks per item, A/B on one B200, whole op: 8 warps x 3 CTAs/SM 115.7 us,
+  //  6 x 4: 115.7, 5 x 5 (no idle task slot in the last round): 119.8 — the end-of-item barrier is not what binds it;
+  //  one-bin-per-warp form, 7 warps with round-robin bins: 124-127 vs 121 for 8 warps + smem counter)
+  const int threads = 256;
   const int grid = (int)std::min<long long>(items_ll, (long long)sms * (pair ? 3 : 4));
   // (measured on B200, cfg2, gather only: 16 taps per bin straight from per-CTA tables 106 us; taps merged per bin
   //  95 us; tables moved to the prologue, no other change 90 us; 8 loads per step actually in flight (see the
