@@ -198,6 +198,26 @@ __host__ __device__ inline size_t roi_table_stride(int nbins, int sampling_ratio
   return 16 + (size_t)((nbins + 3) & ~3) * 4 + (size_t)nbins * roi_table_fstride(sampling_ratio) * sizeof(int2);
 }
 
+// Work-queue block behind the tables: int ctr[64] (ctr[0] = the gather's item counter, ctr[16 + b] = RoIs in cost
+// bucket b) and int order[kRoiBuckets][R] (the RoIs of bucket b in arrival order).  The gather walks the buckets from
+// the most expensive RoIs to the cheapest (longest-processing-time-first): with RoIs taken in input order the last
+// work items of the persistent CTAs are as likely large as small and 14 % of the kernel was tail (ncu: SM active
+// 127k of 148k cycles; handing the same RoIs over largest-first: 115.7 -> 107.5 us for the whole op).
+constexpr int kRoiBuckets = 8;
+__host__ __device__ inline size_t roi_queue_bytes(int R) { return 256 + (((size_t)kRoiBuckets * (R > 0 ? R : 0) * 4 + 255) & ~(size_t)255); }
+__device__ __forceinline__ int roi_cost_bucket(int taps) { return max(0, kRoiBuckets - 1 - taps / 96); }   // 0 = most taps (<= 784)
+// rank-th RoI in bucket order (rank < R)
+__device__ __forceinline__ int roi_by_rank(const int* __restrict__ ctr, int R, int rank) {
+  const int* order = ctr + 64;
+#pragma unroll
+  for (int b = 0; b < kRoiBuckets; b++) {
+    const int n = ctr[16 + b];
+    if (rank < n) return order[(size_t)b * R + rank];
+    rank -= n;
+  }
+  return 0;   // unreachable when the buckets hold all R RoIs
+}
+
 __device__ __forceinline__ void relayout_tile(const float* __restrict__ in, float* __restrict__ out, int C, int HW, int b,
                                               int p0, int c0, float (*tile)[33]) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -261,7 +281,6 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
                                                             unsigned char* __restrict__ tables, bool vec,
                                                             int* __restrict__ work_counter, const __grid_constant__ RoiLevels L) {
   extern __shared__ __align__(16) unsigned char smem[];
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *work_counter = 0;   // the gather's work queue (next launch on the stream)
   if ((int)blockIdx.x < tiles_x) {
     const int b = tiles_y > 0 ? blockIdx.y / tiles_y : 0, ty = blockIdx.y - b * tiles_y;
     if (vec) relayout_tile_v4(in, nhwc, C, H * W, b, blockIdx.x * kTileW, ty * 32, reinterpret_cast<float(*)[kTileW + 1]>(smem));
@@ -302,6 +321,17 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
   const size_t stride = roi_table_stride(nbins, sample_num);
   int4* dst = reinterpret_cast<int4*>(tables + (size_t)idx * stride);
   for (int i = threadIdx.x; i < (int)(stride / 16); i += blockDim.x) dst[i] = hdr[i];
+  if (threadIdx.x < 32) {   // cost = merged taps of the RoI -> its bucket of the gather's work queue (counters zeroed by the host side's memset)
+    int taps = 0;
+    for (int b = threadIdx.x; b < nbins; b += 32) taps += cnt[b];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) taps += __shfl_xor_sync(0xffffffffu, taps, d);
+    if (threadIdx.x == 0) {
+      const int b = roi_cost_bucket(taps);
+      const int pos = atomicAdd(work_counter + 16 + b, 1);
+      work_counter[64 + (size_t)b * R + pos] = (int)idx;
+    }
+  }
 }
 
 // ---- gather kernel ------------------------------------------------------------------------------------
@@ -334,13 +364,17 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
   // NEXT item is fetched by a bulk-async copy while the current one is gathered, and the slab store of the
   // PREVIOUS item drains while the current one runs — a CTA never sits waiting for its 6.7 KB table or its store.
   int cur = blockIdx.x;                                            // first item: static; later ones from the counter
+  const int R = items / nslabs;
+  __shared__ int s_roi[2];                                         // RoI of the item whose table sits in rec buffer 0 / 1
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     mbar_init_fence();
     if (cur < items) {
+      const int roi = roi_by_rank(work_counter, R, cur / nslabs);
+      s_roi[0] = roi;
       mbar_expect_tx(&full[0], (uint32_t)stride);
-      bulk_g2s(rec_base, tables + (size_t)(cur / nslabs) * stride, (uint32_t)stride, &full[0]);
+      bulk_g2s(rec_base, tables + (size_t)roi * stride, (uint32_t)stride, &full[0]);
     }
   }
   __syncthreads();
@@ -357,11 +391,13 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
       const int nx = atomicAdd(work_counter, 1) + (int)gridDim.x;
       s_next_item = nx;                                            // read by everyone after the barrier before the store
       if (nx < items) {
+        const int roi = roi_by_rank(work_counter, R, nx / nslabs);
+        s_roi[buf ^ 1] = roi;                                      // (slot buf ^ 1 was last read before the barrier above)
         mbar_expect_tx(&full[buf ^ 1], (uint32_t)stride);
-        bulk_g2s(rec_base + (buf ^ 1) * stride, tables + (size_t)(nx / nslabs) * stride, (uint32_t)stride, &full[buf ^ 1]);
+        bulk_g2s(rec_base + (buf ^ 1) * stride, tables + (size_t)roi * stride, (uint32_t)stride, &full[buf ^ 1]);
       }
     }
-    const int r = cur / nslabs, c0 = (cur - r * nslabs) * SLAB;
+    const int r = s_roi[buf], c0 = (cur % nslabs) * SLAB;
     const int4* rec = reinterpret_cast<const int4*>(rec_base + buf * stride);
     const int batch = rec[0].x, fstride = rec[0].z;
     const float count = __int_as_float(rec[0].y);
@@ -742,6 +778,7 @@ static cudaError_t launch_staged(int version, const float* input_nchw, const flo
                                  float spatial_scale, int sampling_ratio, float* output, cudaStream_t st) {
   const size_t stride = roi_table_stride(PH * PW, sampling_ratio);
   int* work_counter = reinterpret_cast<int*>(tables + jdet_align_up((size_t)R * stride, 256));
+  { cudaError_t e0 = cudaMemsetAsync(work_counter, 0, 256, st); if (e0 != cudaSuccess) return e0; }   // item counter + bucket counts
   RoiLevels L{};
   L.n = 1;
   L.lv[0] = RoiLevel{input_nchw ? nhwc_scratch : nhwc_in, H, W, spatial_scale};
@@ -757,12 +794,12 @@ JDET_API size_t jdet_roi_align_rotated_workspace_bytes(int B, int C, int H, int 
                                                        int sampling_ratio) {
   if (!jdet::use_staged(B, C, H, W, R, PH, PW, sampling_ratio)) return 256;
   return jdet_align_up((size_t)B * C * H * W * sizeof(float), 256) +          // channel-last copy
-         jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256) + 256;   // tap tables + work counter
+         jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256) + jdet::roi_queue_bytes(R);   // tap tables + work queue
 }
 
 JDET_API size_t jdet_roi_align_rotated_nhwc_workspace_bytes(int R, int PH, int PW, int sampling_ratio) {
   if (sampling_ratio <= 0 || R <= 0 || PH <= 0 || PW <= 0) return 256;
-  return jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256) + 256;
+  return jdet_align_up((size_t)R * jdet::roi_table_stride(PH * PW, sampling_ratio), 256) + jdet::roi_queue_bytes(R);
 }
 
 // version 1: ROIAlignRotated_v1 / roi_align (ops/roi_align_rotated_v1.py:300-326,355-365)
@@ -822,7 +859,7 @@ JDET_API size_t jdet_roi_align_rotated_fpn_workspace_bytes(int nlevels, int B, i
   if (nlevels <= 0 || !Hs || !Ws || sampling_ratio <= 0 || PH <= 0 || PW <= 0) return 256;
   size_t total = 0;
   for (int l = 0; l < nlevels; l++) total += jdet_align_up((size_t)B * C * Hs[l] * Ws[l] * sizeof(float), 256);
-  return total + jdet_align_up((size_t)(R > 0 ? R : 0) * jdet::roi_table_stride(PH * PW, sampling_ratio), 256) + 256;
+  return total + jdet_align_up((size_t)(R > 0 ? R : 0) * jdet::roi_table_stride(PH * PW, sampling_ratio), 256) + jdet::roi_queue_bytes(R);
 }
 
 JDET_API int jdet_roi_align_rotated_fpn(int version, const float* const* feats, int nlevels, int B, int C, const int* Hs,
@@ -850,6 +887,7 @@ JDET_API int jdet_roi_align_rotated_fpn(int version, const float* const* feats, 
   }
   unsigned char* tables = p;
   int* work_counter = reinterpret_cast<int*>(tables + jdet_align_up((size_t)R * roi_table_stride(PH * PW, sampling_ratio), 256));
+  JDET_RETURN_IF_CUDA(cudaMemsetAsync(work_counter, 0, 256, st));   // item counter + bucket counts
   for (int l = 0; l < nlevels; l++)
     JDET_RETURN_IF_CUDA(launch_prologue(version, feats[l], const_cast<float*>(L.lv[l].nhwc), B, C, Hs[l], Ws[l], l == 0, tables,
                                         work_counter, rois, R, PH, PW, sampling_ratio, L, st));

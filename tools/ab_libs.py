@@ -99,6 +99,15 @@ def worker(ops_sel):
         rois = cu(np.concatenate([np.zeros((2048, 1), np.float32), dota_boxes(rng, 2048, 1024.0)], 1))
         res["roi_cfg2_us"] = timeit(lambda: ops.roi_align_rotated_v1.roi_align(feat, rois, (7, 7), 0.25, 2), 30)
         res["roi_cfg2_hash"] = h(ops.roi_align_rotated_v1.roi_align(feat, rois, (7, 7), 0.25, 2))
+        # the same RoIs handed over largest first / smallest first: how much of the time is the tail of the work queue?
+        area = rois[:, 3] * rois[:, 4]
+        big = rois[torch.argsort(area, descending=True)].contiguous()
+        small = rois[torch.argsort(area)].contiguous()
+        res["roi_cfg2_largest_first_us"] = timeit(lambda: ops.roi_align_rotated_v1.roi_align(feat, big, (7, 7), 0.25, 2), 30)
+        res["roi_cfg2_smallest_first_us"] = timeit(lambda: ops.roi_align_rotated_v1.roi_align(feat, small, (7, 7), 0.25, 2), 30)
+        fcl = feat.contiguous(memory_format=torch.channels_last)
+        res["roi_cfg2_channels_last_us"] = timeit(lambda: ops.roi_align_rotated_v1.roi_align(fcl, rois, (7, 7), 0.25, 2), 30)
+        res["roi_cfg2_channels_last_largest_first_us"] = timeit(lambda: ops.roi_align_rotated_v1.roi_align(fcl, big, (7, 7), 0.25, 2), 30)
     print(json.dumps(res), flush=True)
 
 
