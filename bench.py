@@ -188,16 +188,18 @@ def run_ours(args):
     alg_bytes = feat.numel() * 4 + rois.numel() * 4 + out.numel() * 4        # 169 918 464 B
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm",
-                "kernel": "roi_align_rotated = roi_prologue_kernel<1> (re-layout + tap tables) + roi_gather_kernel<16, true> "
-                          "(2 launches per step; the duration used is the WHOLE step, dominant kernel = the gather, ~69 % of it)",
+                "kernel": "roi_align_rotated = roi_prologue_kernel<1> (re-layout + tap tables + cost buckets) + roi_gather_kernel<16, true> "
+                          "(2 kernel launches + one 256-B memset node per step; the duration used is the WHOLE step, dominant "
+                          "kernel = the gather, ~66 % of it)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "peak_source": peaks["source"], "algorithmic_bytes": alg_bytes,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels from the committed ncu --set full
-                # capture (profiles/r01_ncu_summary.md, cold L2): prologue 67.2 + 31.8 MB, gather 134.9 + 73.4 MB
-                "traffic": 306_600_000,
-                "note": "the gather is bound by the SM's L1 data path and issue slots (l1tex 57 %, issue 60 %, no DRAM/L2 "
-                        "limit in sight: an L2-resident random 1-KB gather probe reaches 19-20 TB/s on this GPU, "
-                        "profiles/r01_l2_gather_probe.txt); 0.80 GB of taps cross L1 per launch after per-bin merging"}
+                # capture (profiles/r01_ncu_reentry_selected_metrics.csv, cold L2): prologue 67.2 + 31.7 MB, gather 114.1 + 53.0 MB
+                "traffic": 266_000_000,
+                "note": "latency-bound, no unit saturated (ncu: l1tex 43-53 %, issue slots 47 %, 43 % of stall samples wait on "
+                        "loads, L1 hit 45-58 %, DRAM 33 %): 0.80 GB of merged taps cross L1 per launch for 170 MB of algorithmic "
+                        "bytes; an L2-resident random 1-KB gather probe reaches 19-20 TB/s on this GPU "
+                        "(profiles/r01_l2_gather_probe.txt)"}
 
     # ---- e2e: host buffers, H2D + op + D2H inside the timed region ----------------------------
     # Three streams (H2D / op / D2H), two buffers: step i+1's upload overlaps step i's op and download

@@ -47,6 +47,29 @@ def test_iou_bit_exact_vs_oracle(version, shape):
     assert len(bad[0]) == 0, (len(bad[0]), got[bad][:5], want[bad][:5])
 
 
+def _lattice_boxes(rng, n):
+    """Integer-lattice boxes at multiples of 45 degrees: shared corners, collinear / parallel edges, exact zeros in the
+    edge tests, up to 24 (duplicate) clip points — the exact routine's fallback and slot-overflow paths, and the pairs
+    on which the reference's own hull overshoots the true IoU."""
+    return np.stack([rng.integers(0, 6, n), rng.integers(0, 6, n), rng.integers(1, 5, n), rng.integers(1, 5, n),
+                     rng.integers(-4, 5, n) * (np.pi / 4)], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("version", [0, 1])
+def test_iou_dense_tiles_and_degenerate_pairs(version):
+    """Tiles whose 8192 pairs ALL survive the reject stages (several rounds of the 4096-entry survivor queue) and
+    lattice boxes (comparison-only unit tests leave their ordinary range; more clip points than shared-memory slots)."""
+    rng = np.random.default_rng(21 + version)
+    heap = clustered_boxes(rng, 450, 450, 100.0)              # one cluster: every pair overlaps
+    lat = _lattice_boxes(rng, 300)
+    fn = ops().box_iou_rotated if version == 0 else ops().box_iou_rotated_v1
+    for b1, b2 in ((heap[:192], heap[192:]), (lat[:130], lat), (lat, heap[:140])):
+        got = fn(cu(b1), cu(b2)).cpu().numpy()
+        want = oracle.box_iou_rotated(b1, b2, version, oracle.VARIANT_CUDA)
+        bad = np.nonzero(bits(got) != bits(want))
+        assert len(bad[0]) == 0, (len(bad[0]), got[bad][:5], want[bad][:5])
+
+
 def test_iou_golden_and_known_answers():
     g = np.load(os.path.join(GOLD, "ref_cpu_iou.npz"))
     b1, b2 = cu(g["boxes1"]), cu(g["boxes2"])
@@ -109,6 +132,22 @@ def test_iou_full_size_properties():
 
 
 # ------------------------------------------------------------------------------------ NMS
+@pytest.mark.parametrize("thr", [0.1, 0.26, 0.5])
+def test_nms_lattice_boxes_where_the_reference_hull_overshoots(thr):
+    """Parallel / perpendicular lattice pairs are exempt from the IoU-upper-bound pruning because the reference's IoU
+    can exceed the true one there (0.2635 vs 0.25 straddles thr = 0.26): keep flags must still equal the oracle's."""
+    rng = np.random.default_rng(9)
+    d = np.concatenate([_lattice_boxes(rng, 900), np.array([[3, 2, 4, 3, 3 * np.pi / 4], [4, 1, 3, 1, -3 * np.pi / 4]], np.float32)])
+    s = tie_free_scores(rng, len(d))
+    s[-2], s[-1] = 2.0, 1.5                                   # the overshooting pair first, in (a, b) order
+    l = rng.integers(0, 2, len(d)).astype(np.int64)
+    l[-2:] = 0
+    got = ops().nms_rotated.ml_nms_rotated(cu(d), cu(s), cu(l, torch.int64), thr).cpu().numpy()
+    assert np.array_equal(got, oracle.ml_nms_rotated(d, s, l, thr, oracle.VARIANT_CUDA))
+    got5 = ops().nms_rotated.nms_rotated(cu(d), cu(s), thr).cpu().numpy()
+    assert np.array_equal(got5, oracle.nms_rotated(d, s, thr, oracle.VARIANT_CUDA))
+
+
 def _nms_case(rng, n, ncls, clustered=True):
     d = clustered_boxes(rng, n, 25, 512.0) if clustered else dota_boxes(rng, n, 512.0)
     return d, tie_free_scores(rng, n), rng.integers(0, ncls, n).astype(np.int64)
