@@ -373,7 +373,9 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(
     int n, const int* __restrict__ sorted_idx, const unsigned long long* __restrict__ mask,
     unsigned char* __restrict__ keep) {
   extern __shared__ unsigned long long s_kept[];       // [W]
-  __shared__ volatile int s_progress;                   // number of column blocks resolved so far
+  __shared__ int s_progress;                            // number of column blocks resolved so far: written with
+                                                        // st.release.cta, polled with ld.acquire.cta (kept(cb) is
+                                                        // published before the counter moves past cb)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nseg = scan[n - 1];
   for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
@@ -402,8 +404,7 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(
         for (int b = 0; b < kScanBatch; b++) {
           if (b < nb) {
             const int rb = rb0 + b;
-            while (s_progress <= rb) { }                                  // kept(rb) not published yet
-            __threadfence_block();
+            while (ld_acquire_cta(&s_progress) <= rb) { }                 // kept(rb) not published yet
             const unsigned long long k = s_kept[rb];
             unsigned long long v = 0ull;
             if ((k >> lane) & 1ull) v |= w0[b];
@@ -432,10 +433,9 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(
       const unsigned long long vmask = valid >= 64 ? ~0ull : ((1ull << valid) - 1ull);
       const unsigned long long kept = ~cur & vmask;
       if (lane == 0) {
-        while (s_progress < cb) { }                       // publish strictly in order
+        while (ld_acquire_cta(&s_progress) < cb) { }      // publish strictly in order
         s_kept[cb] = kept;
-        __threadfence_block();
-        s_progress = cb + 1;
+        st_release_cta(&s_progress, cb + 1);
       }
       if ((kept >> lane) & 1ull) keep[idx0] = 1;
       if ((kept >> (lane + 32)) & 1ull) keep[idx1] = 1;
