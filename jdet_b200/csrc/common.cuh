@@ -62,17 +62,6 @@ __device__ __forceinline__ void ldg_v4_keep(float4& v, const float* p, bool live
       : "l"(p), "r"((int)live));
 }
 
-// flag hand-off between warps of one CTA through shared memory (producer: data stores, then st_release_cta(flag);
-// consumer: spin on ld_acquire_cta(flag), then read the data)
-__device__ __forceinline__ int ld_acquire_cta(const int* p) {
-  int v;
-  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_cta(int* p, int v) {
-  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
-
 // ---- mbarrier / bulk-async-copy helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
