@@ -69,7 +69,10 @@ int jdet_argsort_desc(const float* scores, int n, int* order, void* workspace, s
  * replaces: version 1: _RotatedROIAlign_v1.execute ops/roi_align_rotated_v1.py:300-326 (kernel :70-147)
  *           version 0: _RotatedROIAlign.execute    ops/roi_align_rotated.py:257-283   (kernel :60-127)
  * input (B,C,H,W); rois (R,6) = [batch, x_ctr, y_ctr, w, h, theta]; output (R,C,PH,PW).
- * sampling_ratio: the int the reference kernel receives (<= 0: adaptive ceil(roi/pooled) grid).    */
+ * sampling_ratio: the int the reference kernel receives (<= 0: adaptive ceil(roi/pooled) grid).
+ * Dense RoI sets take the staged path (workspace = channel-last copy of the map + per-RoI tap tables + the gather's
+ * work queue: a 256-B counter block, zeroed by the call itself with one memset node, and 8 x R RoI indices); it
+ * needs H*W*C < 2^30 per image (tap tables hold 32-bit byte offsets), else cudaErrorInvalidConfiguration.        */
 size_t jdet_roi_align_rotated_workspace_bytes(int B, int C, int H, int W, int R, int PH, int PW,
                                               int sampling_ratio);
 int jdet_roi_align_rotated(int version, const float* input, int B, int C, int H, int W, const float* rois,
@@ -77,7 +80,7 @@ int jdet_roi_align_rotated(int version, const float* input, int B, int C, int H,
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* same op for a feature map that is ALREADY channel-last in memory, (B,H,W,C) — e.g. a torch channels_last
- * tensor out of the FPN convolutions: no re-layout pass; the workspace only holds the per-RoI tap tables.  Needs C % 64 == 0, sampling_ratio > 0 and
+ * tensor out of the FPN convolutions: no re-layout pass; the workspace only holds the per-RoI tap tables and the work queue.  Needs C % 64 == 0, sampling_ratio > 0 and
  * PH*PW*sampling_ratio^2 <= 1024; otherwise JDET_ERR_UNSUPPORTED (callers fall back to the NCHW entry point). */
 size_t jdet_roi_align_rotated_nhwc_workspace_bytes(int R, int PH, int PW, int sampling_ratio);
 int jdet_roi_align_rotated_nhwc(int version, const float* input_nhwc, int B, int C, int H, int W, const float* rois,

@@ -31,7 +31,13 @@ namespace jdet {
 constexpr int kCH = 16;            // column blocks per work item (64 rows x 1024 columns)
 constexpr int kColsPerThread = kCH * 64 / 256;
 constexpr int kMaskThreads = 256;
-constexpr int kQCap = 4096;        // survivor queue entries per CTA (overflow => extra rounds)
+#ifndef JDET_NMS_QCAP
+#define JDET_NMS_QCAP 4096
+#endif
+#ifndef JDET_NMS_MASK_MINB
+#define JDET_NMS_MASK_MINB 3
+#endif
+constexpr int kQCap = JDET_NMS_QCAP;   // survivor queue entries per CTA (overflow => extra rounds)
 
 struct NmsWs {
   unsigned* keys_in; unsigned* keys_out; int* vals_in; int* vals_out;
@@ -141,7 +147,7 @@ __device__ __forceinline__ long long tri_index(long long rb, long long cb) { ret
 //   phase 1  thread <-> 2 columns (registers), loop over the 64 rows (broadcast LDS.128): circle test
 //   phase 2  SAT on compacted survivors          phase 3  exact IoU, strict "> thr", bits via smem atomics
 // label_in_pair != 0 (thr < 0 corner): single segment, no quick rejects, label mismatch => IoU 0.
-__global__ void __launch_bounds__(kMaskThreads, 3) nms_mask_kernel(
+__global__ void __launch_bounds__(kMaskThreads, JDET_NMS_MASK_MINB) nms_mask_kernel(
     const BoxRec* __restrict__ rec, const int* __restrict__ seg_start, const int* __restrict__ item_base,
     const long long* __restrict__ tile_base, const int* __restrict__ scan, int n, float thr,
     int flags, int* __restrict__ counter, unsigned long long* __restrict__ mask,
@@ -523,7 +529,7 @@ JDET_API int jdet_nms_rotated_ex(const float* dets, int n, int box_length, const
   }
   const size_t mask_smem = (size_t)(64 + kCH * 64) * sizeof(BoxRec) + 64 * 16 + (size_t)kCH * 64 * 2 * 4 + (size_t)kQCap * 2 * 2;
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_smem));
-  nms_mask_kernel<<<kNumSMs * 3, kMaskThreads, mask_smem, st>>>(w.rec, w.seg_start, w.item_base, w.tile_base,
+  nms_mask_kernel<<<kNumSMs * JDET_NMS_MASK_MINB, kMaskThreads, mask_smem, st>>>(w.rec, w.seg_start, w.item_base, w.tile_base,
                                                         w.flag_scan, n, iou_threshold, flags,
                                                         w.counters, w.mask, w.xqueue, w.xcap);
   const size_t exact_smem = (size_t)3 * kExactCap * 256 * sizeof(float);

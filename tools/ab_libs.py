@@ -122,8 +122,10 @@ if __name__ == "__main__":
         if args and args[0] == "--ops":
             ops_sel, args = args[1], args[2:]
         names = args or sorted(f[3:-3] for f in os.listdir(AB) if f.endswith(".so"))
-        for name in [None] + names:
+        order = names if "tree" in names else ["tree"] + names      # "tree" may be placed explicitly (first process on a cold box runs slow)
+        for name in order:
             env = dict(os.environ)
-            if name:
+            env.pop("JDET_B200_LIB", None)
+            if name != "tree":
                 env["JDET_B200_LIB"] = os.path.join(AB, "lib%s.so" % name)
             subprocess.call([sys.executable, os.path.abspath(__file__), "worker", ops_sel], env=env)
