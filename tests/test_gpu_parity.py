@@ -70,6 +70,19 @@ def test_iou_dense_tiles_and_degenerate_pairs(version):
         assert len(bad[0]) == 0, (len(bad[0]), got[bad][:5], want[bad][:5])
 
 
+def test_iou_candidate_queue_overflow():
+    """4200 x 4200 boxes of ONE cluster: 17.6 M overlapping pairs, more than the 16 M slots of the device-wide
+    candidate queue, so the last tile CTAs evaluate their own candidates in place (compact routine) and the exact
+    kernel skips the reserved-but-unused slots.  Bit-exact against the oracle all the same."""
+    rng = np.random.default_rng(3)
+    b = clustered_boxes(rng, 4200, 4200, 100.0)
+    got = ops().box_iou_rotated(cu(b), cu(b)).cpu().numpy()
+    want = oracle.box_iou_rotated(b, b, 0, oracle.VARIANT_CUDA)
+    assert (want > 0).mean() > 0.99
+    bad = np.nonzero(bits(got) != bits(want))
+    assert len(bad[0]) == 0, (len(bad[0]), got[bad][:5], want[bad][:5])
+
+
 def test_iou_golden_and_known_answers():
     g = np.load(os.path.join(GOLD, "ref_cpu_iou.npz"))
     b1, b2 = cu(g["boxes1"]), cu(g["boxes2"])
@@ -146,6 +159,16 @@ def test_nms_lattice_boxes_where_the_reference_hull_overshoots(thr):
     assert np.array_equal(got, oracle.ml_nms_rotated(d, s, l, thr, oracle.VARIANT_CUDA))
     got5 = ops().nms_rotated.nms_rotated(cu(d), cu(s), thr).cpu().numpy()
     assert np.array_equal(got5, oracle.nms_rotated(d, s, thr, oracle.VARIANT_CUDA))
+
+
+def test_nms_candidate_queue_overflow():
+    """4400 boxes of one cluster, one class, thr 0.05: ~9.7 M same-class pairs that survive every reject stage, more
+    than the 8 M slots of the exact-IoU candidate queue — the mask kernel then evaluates its own candidates."""
+    rng = np.random.default_rng(4)
+    d, s = clustered_boxes(rng, 4400, 4400, 100.0), tie_free_scores(rng, 4400)
+    for thr in (0.05, 0.3, 0.6):   # (the higher thresholds prune more pairs before the queue and keep more boxes)
+        got = ops().nms_rotated.nms_rotated(cu(d), cu(s), thr).cpu().numpy()
+        assert np.array_equal(got, oracle.nms_rotated(d, s, thr, oracle.VARIANT_CUDA)), thr
 
 
 def _nms_case(rng, n, ncls, clustered=True):
