@@ -11,15 +11,17 @@
 //
 // Kernel 1  rec_kernel        one thread per box: double-precision cos/sin hoisted out of the
 //                             N*M loop (the reference recomputes them per pair), circumradius.
-// Kernel 2  iou_tile_kernel   CTA = 64 x 128 output tile, 256 threads.
-//     phase 1  every pair: circle test from registers/smem, 16-B streaming stores of +0.0;
-//              survivors are recorded in a per-thread 32-bit mask, then compacted into a
-//              shared-memory queue with one warp scan + one atomic per warp.
+// Kernel 2  iou_tile_kernel   CTA = 64 x 128 output tile, 256 threads, 8 CTAs per SM.
+//     phase 1  every pair: circle test whose verdict is a sign bit funnel-shifted into a per-thread
+//              32-bit mask (7 issue slots per pair), 16-B streaming stores of +0.0; survivors are
+//              compacted into a 4096-entry shared-memory queue (one warp scan + one atomic per warp),
+//              in rounds when a tile has more.
 //     phase 2  queue -> SAT test -> second queue (warp-aggregated push).
 //              The surviving (row, col) candidates are appended to a device-wide queue.
 // Kernel 3  iou_exact_kernel  one thread per queued candidate (grid-stride over the device-side count):
-//                             reference-exact clip/hull IoU with every lane busy and no barriers,
-//                             4-B stores over the zeros.  (Queue full => the tile CTA evaluates its own.)
+//                             reference-exact clip/hull IoU (straight-line edge stage, clip points in a
+//                             [slot][thread] shared-memory array), every lane busy, no barriers, 4-B stores
+//                             over the zeros.  (Queue full => the tile CTA evaluates its own.)
 #include "common.cuh"
 #include "rbox_geom.cuh"
 
