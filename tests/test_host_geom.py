@@ -4,8 +4,7 @@ bit.  This is what lets the device routine be restructured without a GPU in the 
 proof for the device build itself."""
 import ctypes
 import os
-import shutil
-import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -13,23 +12,19 @@ import pytest
 import oracle
 from _inputs import ADVERSARIAL, clustered_boxes, dota_boxes
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "host", "host_geom.cu")
-HDR = os.path.join(HERE, "..", "jdet_b200", "csrc", "rbox_geom.cuh")
-SO = os.path.join(HERE, "_build", "libhostgeom.so")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host"))
+import host_geom_build as host_build  # noqa: E402
+
 fp = ctypes.POINTER(ctypes.c_float)
 ip = ctypes.POINTER(ctypes.c_int)
 
 
 @pytest.fixture(scope="module")
 def hg():
-    if shutil.which("nvcc") is None:
+    so = host_build.build()
+    if so is None:
         pytest.skip("nvcc not on PATH")
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
-        os.makedirs(os.path.dirname(SO), exist_ok=True)
-        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off",
-                               "-gencode", "arch=compute_100a,code=sm_100a", SRC, "-o", SO])
-    return ctypes.CDLL(SO)
+    return ctypes.CDLL(so)
 
 
 def bits(a):
