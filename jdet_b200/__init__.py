@@ -17,7 +17,7 @@ def install_as_jdet():
     pkg = sys.modules[__name__]
     sys.modules.setdefault("jdet", pkg)
     for sub in ("ops", "ops.box_iou_rotated", "ops.box_iou_rotated_v1", "ops.nms_rotated", "ops.roi_align_rotated",
-                "ops.roi_align_rotated_v1", "ops.fr", "ops.dcn_v1", "models", "models.roi_heads",
+                "ops.roi_align_rotated_v1", "ops.fr", "ops.dcn_v1", "ops.orn", "ops.bbox_transforms", "models", "models.roi_heads",
                 "models.roi_heads.s2anet_head", "models.roi_extractors", "models.boxes",
                 "models.boxes.iou_calculator"):
         try:

@@ -5,4 +5,4 @@ submodules (``from jdet_b200.ops import roi_align_rotated_v1`` -> module), as in
 """
 from .box_iou_rotated import box_iou_rotated
 from .box_iou_rotated_v1 import box_iou_rotated_v1
-from . import nms_rotated, roi_align_rotated, roi_align_rotated_v1, fr, dcn_v1, orn  # noqa: F401
+from . import nms_rotated, roi_align_rotated, roi_align_rotated_v1, fr, dcn_v1, orn, bbox_transforms  # noqa: F401
