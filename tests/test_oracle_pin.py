@@ -97,6 +97,26 @@ def test_against_compiled_reference_random():
     assert np.array_equal(keep, oracle.nms_rotated_keep(d6, order, 0.2, oracle.VARIANT_CPU))
 
 
+def test_reference_hull_overshoot_pair():
+    """The reference's own arithmetic overshoots the true IoU on this lattice pair (b lies inside a with two collinear
+    edges: true IoU 0.25): both of its builds return 0.26354942 in (a, b) order and 0.25 in (b, a) order.  The oracle
+    must reproduce that, because the product's NMS pruning exemption for parallel pairs exists for exactly this."""
+    a = np.array([3, 2, 4, 3, 3 * np.pi / 4], np.float32)
+    b = np.array([4, 1, 3, 1, -3 * np.pi / 4], np.float32)
+    for variant in (oracle.VARIANT_CPU, oracle.VARIANT_CUDA):
+        assert np.float32(oracle.single_iou(a, b, 0, variant)) == np.float32(0.26354942)
+        assert np.float32(oracle.single_iou(b, a, 0, variant)) == np.float32(0.25)
+    RC = oracle.ref_cpu()
+    if RC is not None:   # the reference's compiled CPU source says the same
+        assert np.float32(RC.ref_single_iou_v0_cpu(a.ctypes.data_as(fp), b.ctypes.data_as(fp))) == np.float32(0.26354942)
+        assert np.float32(RC.ref_single_iou_v0_cpu(b.ctypes.data_as(fp), a.ctypes.data_as(fp))) == np.float32(0.25)
+    RG = oracle.ref_cuda()
+    if RG is not None and hasattr(RG, "ref_single_iou_v0_cudavariant_host"):   # and so does its CUDA-variant source run on the host
+        f = RG.ref_single_iou_v0_cudavariant_host
+        f.restype = ctypes.c_float
+        assert np.float32(f(a.ctypes.data_as(fp), b.ctypes.data_as(fp))) == np.float32(0.26354942)
+
+
 def test_v1_small_box_zeroing():
     b = np.array([[0, 0, 4, 4, 0.1], [1, 1, 5e-4, 4, 0.2], [0.5, 0, 3, 3, -0.1]], np.float32)
     out = oracle.box_iou_rotated(b, b, version=1)
