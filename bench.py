@@ -199,7 +199,7 @@ def run_ours(args):
     roofline = {"bound": "hbm",
                 "kernel": "roi_align_rotated = roi_prologue_kernel<1> (re-layout + tap tables + cost buckets) + roi_gather_kernel<16, true> "
                           "(2 kernel launches + one 256-B memset node per step; the duration used is the WHOLE step, dominant "
-                          "kernel = the gather, ~66 % of it)",
+                          "kernel = the gather, ~69 % of it: 71.9 of 103.4 us in the ncu launch list, profiles/r01_launches_reentry.md)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "peak_source": peaks["source"], "algorithmic_bytes": alg_bytes,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels from the committed ncu --set full
