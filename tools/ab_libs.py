@@ -121,7 +121,7 @@ if __name__ == "__main__":
         ops_sel = "iou,nms,roi"
         if args and args[0] == "--ops":
             ops_sel, args = args[1], args[2:]
-        names = args or sorted(f[3:-3] for f in os.listdir(AB) if f.endswith(".so"))
+        names = args or (sorted(f[3:-3] for f in os.listdir(AB) if f.endswith(".so")) if os.path.isdir(AB) else [])
         order = names if "tree" in names else ["tree"] + names      # "tree" may be placed explicitly (first process on a cold box runs slow)
         for name in order:
             env = dict(os.environ)
