@@ -22,6 +22,8 @@
 //                             reference-exact clip/hull IoU (straight-line edge stage, clip points in a
 //                             [slot][thread] shared-memory array), every lane busy, no barriers, 4-B stores
 //                             over the zeros.  (Queue full => the tile CTA evaluates its own.)
+#include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "rbox_geom.cuh"
 
@@ -40,9 +42,9 @@ constexpr int kQCap = JDET_IOU_QCAP;        // survivor queue entries per round 
 // both box sets in one launch (small problems are launch-bound); also resets the candidate counter
 __global__ void __launch_bounds__(256) rec_kernel(const float* __restrict__ boxes1, int n1, const float* __restrict__ boxes2,
                                                   int n2, int zero_small, BoxRec* __restrict__ rec1,
-                                                  BoxRec* __restrict__ rec2, int* __restrict__ gcount) {
+                                                  BoxRec* __restrict__ rec2, unsigned long long* __restrict__ gcount) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *gcount = 0;
+  if (i == 0) *gcount = 0ull;
   const float* b;
   BoxRec* dst;
   if (i < n1) { b = boxes1 + (size_t)i * 5; dst = rec1 + i; }
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(256) rec_kernel(const float* __restrict__ boxe
 template <int VERSION, bool VEC4>
 __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(const BoxRec* __restrict__ rec1, int n1,
                                                              const BoxRec* __restrict__ rec2, int n2,
-                                                             float* __restrict__ out, int* __restrict__ gcount,
+                                                             float* __restrict__ out, unsigned long long* __restrict__ gcount,
                                                              uint2* __restrict__ gqueue, int gcap, int variant) {
   __shared__ BoxRec s_row[kTR];
   __shared__ BoxRec s_col[kTC];
@@ -65,7 +67,8 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
   __shared__ float4 s_rq[kTR];                          // rows: (x, y, qr, -) for the broadcast loads of phase 1
   __shared__ unsigned short s_q1[kQCap];
   __shared__ unsigned short s_q2[kQCap];
-  __shared__ int s_cnt1, s_cnt2, s_base;
+  __shared__ int s_cnt1, s_cnt2;
+  __shared__ unsigned long long s_base;               // 64-bit: the reservations of a dense 46k x 46k problem pass 2^31
 
   const int tid = threadIdx.x;
   const int row0 = blockIdx.y * kTR, col0 = blockIdx.x * kTC;
@@ -171,17 +174,17 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
     // ---- hand-off: candidates go to the device-wide queue drained by iou_exact_kernel (every lane of
     // every warp busy there, no barriers); if the queue is full this CTA evaluates its own candidates.
     const int cnt2 = s_cnt2;
-    if (tid == 0) s_base = cnt2 > 0 ? atomicAdd(gcount, cnt2) : 0;
+    if (tid == 0) s_base = cnt2 > 0 ? atomicAdd(gcount, (unsigned long long)cnt2) : 0ull;
     __syncthreads();
-    const int gbase = s_base;
-    if (gbase + cnt2 <= gcap) {
+    const unsigned long long gbase = s_base;
+    if (gbase + (unsigned long long)cnt2 <= (unsigned long long)gcap) {
       for (int k = tid; k < cnt2; k += kThreads) {
         const unsigned short e = s_q2[k];
         gqueue[gbase + k] = make_uint2((unsigned)(row0 + (e >> 7)), (unsigned)(col0 + (e & 127)));
       }
     } else {
       for (int k = tid; k < cnt2; k += kThreads) {
-        if (gbase + k < gcap) gqueue[gbase + k] = make_uint2(0xffffffffu, 0u);   // reserved but unused slot
+        if (gbase + (unsigned long long)k < (unsigned long long)gcap) gqueue[gbase + k] = make_uint2(0xffffffffu, 0u);   // reserved but unused slot
         const unsigned short e = s_q2[k];
         const int r = e >> 7, c = e & 127;
         const BoxRec& A = s_row[r];
@@ -203,12 +206,13 @@ constexpr int kExactThreads = 256;
 constexpr size_t kExactSmem = (size_t)3 * kExactCap * kExactThreads * sizeof(float);
 template <int VERSION>
 __global__ void __launch_bounds__(kExactThreads) iou_exact_kernel(const BoxRec* __restrict__ rec1, const BoxRec* __restrict__ rec2,
-                                                         int n2, const int* __restrict__ gcount,
+                                                         int n2, const unsigned long long* __restrict__ gcount,
                                                          const uint2* __restrict__ gqueue, int gcap,
                                                          float* __restrict__ out, int variant) {
   extern __shared__ float s_pts[];
   float* sq = s_pts + threadIdx.x;
-  const int total = min(*gcount, gcap);
+  const unsigned long long reserved = *gcount;
+  const int total = reserved < (unsigned long long)gcap ? (int)reserved : gcap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint2 e = gqueue[i];
     if (e.x == 0xffffffffu) continue;
@@ -261,9 +265,10 @@ JDET_API int jdet_box_iou_rotated_ex(const float* boxes1, int n1, const float* b
   char* wsp = (char*)workspace;
   BoxRec* rec1 = (BoxRec*)wsp;                 wsp += jdet_align_up((size_t)n1 * sizeof(BoxRec), 256);
   BoxRec* rec2 = (BoxRec*)wsp;                 wsp += jdet_align_up((size_t)n2 * sizeof(BoxRec), 256);
-  int* gcount = (int*)wsp;                     wsp += 256;
+  unsigned long long* gcount = (unsigned long long*)wsp;   wsp += 256;
   uint2* gqueue = (uint2*)wsp;
-  const int gcap = (int)iou_queue_cap(n1, n2);
+  int gcap = (int)iou_queue_cap(n1, n2);
+  if (const char* e = getenv("JDET_TEST_QUEUE_CAP")) gcap = std::max(1, std::min(gcap, atoi(e)));   // tests: force the queue-full path
   rec_kernel<<<jdet_ceil_div(n1 + n2, 256), 256, 0, st>>>(boxes1, n1, boxes2, n2, version == 1, rec1, rec2, gcount);
   dim3 grid(jdet_ceil_div(n2, kTC), jdet_ceil_div(n1, kTR));
   const bool vec = (n2 % 4 == 0) && (((uintptr_t)ious & 15) == 0);

@@ -23,6 +23,8 @@
 #include <cub/cub.cuh>
 
 #include <math.h>
+#include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "rbox_geom.cuh"
 
@@ -43,7 +45,7 @@ struct NmsWs {
   unsigned* keys_in; unsigned* keys_out; int* vals_in; int* vals_out;
   BoxRec* rec; int* sorted_idx; int* flags; int* flag_scan; int* seg_start;
   int* seg_items; int* item_base; long long* seg_tiles; long long* tile_base;
-  int* counters;                   // [0] work counter, [1] candidate-queue count
+  int* counters;                   // [0] work counter; bytes 8..15: the 64-bit candidate-queue reservation count
   uint4* xqueue; int xcap;         // device-wide exact-IoU candidate queue
   unsigned long long* mask; size_t mask_tiles;
   void* cub_temp; size_t cub_bytes;
@@ -70,6 +72,7 @@ static size_t carve(NmsWs* w, void* base, int n) {
   w->cub_temp = take(w->cub_bytes);
   w->xcap = (int)(((long long)n * n / 2 < (8ll << 20)) ? ((long long)n * n / 2 + 64) : (8ll << 20));
   w->xqueue = (uint4*)take((size_t)w->xcap * sizeof(uint4));
+  if (const char* e = getenv("JDET_TEST_QUEUE_CAP")) w->xcap = std::max(1, std::min(w->xcap, atoi(e)));   // tests: force the queue-full path (the layout keeps its full size)
   w->mask_tiles = mask_tile_bound(n);
   w->mask = (unsigned long long*)take(w->mask_tiles * 64 * 8);
   return off;
@@ -161,7 +164,8 @@ __global__ void __launch_bounds__(kMaskThreads, JDET_NMS_MASK_MINB) nms_mask_ker
   unsigned* s_bits = reinterpret_cast<unsigned*>(s_rowq + 64);            //  4 KB: tile words as (lo, hi)
   unsigned short* s_q1 = reinterpret_cast<unsigned short*>(s_bits + kCH * 64 * 2);   // 2 x kQCap entries
   unsigned short* s_q2 = s_q1 + kQCap;
-  __shared__ int s_cnt1, s_cnt2, s_item, s_xbase;
+  __shared__ int s_cnt1, s_cnt2, s_item;
+  __shared__ unsigned long long s_xbase;   // 64-bit: a dense same-class cluster of ~65k boxes reserves more than 2^31 candidates
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int nseg = scan[n - 1];
@@ -299,11 +303,11 @@ __global__ void __launch_bounds__(kMaskThreads, JDET_NMS_MASK_MINB) nms_mask_ker
       // ---- hand-off: exact-IoU candidates go to the device-wide queue (nms_exact_kernel: every lane busy,
       // no barriers).  Queue full => this CTA evaluates its own candidates (phase 3 in place).
       const int c2 = s_cnt2;
-      if (tid == 0) s_xbase = c2 > 0 ? atomicAdd(counter + 1, c2) : 0;
+      if (tid == 0) s_xbase = c2 > 0 ? atomicAdd(reinterpret_cast<unsigned long long*>(counter + 2), (unsigned long long)c2) : 0ull;
       __syncthreads();
-      const int xbase = s_xbase;
+      const unsigned long long xbase = s_xbase;
       const long long wbase = tile_base[seg] * 64;
-      if (xbase + c2 <= xcap) {
+      if (xbase + (unsigned long long)c2 <= (unsigned long long)xcap) {
         for (int k = tid; k < c2; k += kMaskThreads) {
           const unsigned short e = s_q2[k];
           const int r = (e >> 6) & 63, tt = e >> 12, cc = e & 63;
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(kMaskThreads, JDET_NMS_MASK_MINB) nms_mask_ker
         }
       } else {
         for (int k = tid; k < c2; k += kMaskThreads) {
-          if (xbase + k < xcap) xqueue[xbase + k] = make_uint4(0xffffffffu, 0u, 0u, 0u);   // reserved, unused
+          if (xbase + (unsigned long long)k < (unsigned long long)xcap) xqueue[xbase + k] = make_uint4(0xffffffffu, 0u, 0u, 0u);   // reserved, unused
           const unsigned short e = s_q2[k];
           const int r = (e >> 6) & 63, tt = e >> 12, cc = e & 63;
           const BoxRec& A = s_row[r];
@@ -348,7 +352,8 @@ __global__ void __launch_bounds__(256) nms_exact_kernel(const BoxRec* __restrict
   const bool cpu_arith = (flags & 2) != 0;
   extern __shared__ float s_pts[];                     // clip points, [slot][thread]: see iou_exact_shared
   float* sq = s_pts + threadIdx.x;
-  const int total = min(counter[1], xcap);
+  const unsigned long long reserved = *reinterpret_cast<const unsigned long long*>(counter + 2);
+  const int total = reserved < (unsigned long long)xcap ? (int)reserved : xcap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const uint4 e = xqueue[i];
     if (e.x == 0xffffffffu) continue;

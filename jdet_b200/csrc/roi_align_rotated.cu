@@ -23,6 +23,8 @@
 // Layout in HBM: input (B,C,H,W) fp32; rois (R,6) = [batch, cx, cy, w, h, theta]; output
 // (R,C,PH,PW) fp32; workspace: channel-last copy (B*H*W*C fp32) for the staged path.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 
 namespace jdet {
@@ -71,7 +73,8 @@ __device__ __forceinline__ RoiGeom roi_geom(const float* __restrict__ roi, float
 }
 
 // sample point -> taps/weights, following bilinear_interpolate (v1.py:23-68 / .py:21-56)
-template <int VERSION>
+// PACK: the taps name pixels as (y << 16) | x instead of y * W + x (the staged path splits them again without a division)
+template <int VERSION, bool PACK = false>
 __device__ __forceinline__ SampleTap make_tap(const RoiGeom& g, int ph, int pw, int iy, int ix, int H, int W) {
   // same operation order as the reference; explicit _rn ops so no FMA contraction moves a
   // sample across a pixel or validity boundary
@@ -102,7 +105,8 @@ __device__ __forceinline__ SampleTap make_tap(const RoiGeom& g, int ph, int pw, 
   if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
   const float ly = y - (float)yl, lx = x - (float)xl;
   const float hy = 1.f - ly, hx = 1.f - lx;
-  t.o00 = yl * W + xl; t.o01 = yl * W + xh; t.o10 = yh * W + xl; t.o11 = yh * W + xh;
+  if (PACK) { t.o00 = (yl << 16) | xl; t.o01 = (yl << 16) | xh; t.o10 = (yh << 16) | xl; t.o11 = (yh << 16) | xh; }
+  else { t.o00 = yl * W + xl; t.o01 = yl * W + xh; t.o10 = yh * W + xl; t.o11 = yh * W + xh; }
   t.w1 = __fmul_rn(hy, hx); t.w2 = __fmul_rn(hy, lx); t.w3 = __fmul_rn(ly, hx); t.w4 = __fmul_rn(ly, lx);
   return t;
 }
@@ -120,7 +124,7 @@ void launch_nchw_to_nhwc(const float* in, float* out, int B, int C, int HW, cuda
 //           leaders to the front of fin[bin*tpb ..] and cnt[bin] counts them.  The tail is (-1, 0).
 //           Other grid sizes only drop the out-of-range samples (no merging).
 // Ends with a barrier; raw may be reused afterwards.
-template <int VERSION>
+template <int VERSION, bool PACK = false>
 __device__ __forceinline__ void build_tap_table(const RoiGeom& g, int nbins, int PW, int H, int W, int2* raw, int2* fin,
                                                 int fstride, int* cnt, unsigned scale = 1u) {
   // fin holds fstride >= tpb (a multiple of 8) entries per bin: cnt[bin] merged taps (pixel index * scale, weight),
@@ -130,7 +134,7 @@ __device__ __forceinline__ void build_tap_table(const RoiGeom& g, int nbins, int
   const int spb = g.gh * g.gw, tpb = 4 * spb;
   for (int s = threadIdx.x; s < nbins * spb; s += blockDim.x) {
     const int bin = s / spb, k = s - bin * spb;
-    const SampleTap t = make_tap<VERSION>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
+    const SampleTap t = make_tap<VERSION, PACK>(g, bin / PW, bin % PW, k / g.gw, k % g.gw, H, W);
     int4* dst = reinterpret_cast<int4*>(raw + 4 * s);
     dst[0] = make_int4(t.o00, __float_as_int(t.w1), t.o01, __float_as_int(t.w2));
     dst[1] = make_int4(t.o10, __float_as_int(t.w3), t.o11, __float_as_int(t.w4));
@@ -194,9 +198,8 @@ struct RoiLevels { RoiLevel lv[kMaxLevels]; int n; float ext_w, ext_h, rs_w, rs_
 // stream.  One launch does both, interleaved (see the kernel), so the gather CTAs start with nothing but loads
 // to do.
 __host__ __device__ inline int roi_table_fstride(int sampling_ratio) { return (4 * sampling_ratio * sampling_ratio + 7) & ~7; }
-__host__ __device__ inline size_t roi_table_stride(int nbins, int sampling_ratio) {
-  return 16 + (size_t)((nbins + 3) & ~3) * 4 + (size_t)nbins * roi_table_fstride(sampling_ratio) * sizeof(int2);
-}
+__host__ __device__ inline int roi_table_layout_bytes(int nbins, int sampling_ratio);   // record pitch: roi_gather_tma.cuh's rec_layout
+__host__ __device__ inline size_t roi_table_stride(int nbins, int sampling_ratio) { return (size_t)roi_table_layout_bytes(nbins, sampling_ratio); }
 
 // Work-queue block behind the tables: int ctr[64] (ctr[0] = the gather's item counter, ctr[16 + b] = RoIs in cost
 // bucket b) and int order[kRoiBuckets][R] (the RoIs of bucket b in arrival order).  The gather walks the buckets from
@@ -204,7 +207,9 @@ __host__ __device__ inline size_t roi_table_stride(int nbins, int sampling_ratio
 // work items of the persistent CTAs are as likely large as small and 14 % of the kernel was tail (ncu: SM active
 // 127k of 148k cycles; handing the same RoIs over largest-first: 115.7 -> 107.5 us for the whole op).
 constexpr int kRoiBuckets = 8;
-__host__ __device__ inline size_t roi_queue_bytes(int R) { return 256 + (((size_t)kRoiBuckets * (R > 0 ? R : 0) * 4 + 255) & ~(size_t)255); }
+// (+ behind the bucket lists: int staged[R], the RoIs of the TMA-staged path in arrival order, ctr[2] of them, ctr[1] its item
+//  counter; and int rec_bytes[R], the size of each RoI's table record)
+__host__ __device__ inline size_t roi_queue_bytes(int R) { return 256 + (((size_t)(kRoiBuckets + 2) * (R > 0 ? R : 0) * 4 + 255) & ~(size_t)255); }
 __device__ __forceinline__ int roi_cost_bucket(int taps) { return max(0, kRoiBuckets - 1 - taps / 96); }   // 0 = most taps (<= 784)
 // rank-th RoI in bucket order (rank < R)
 __device__ __forceinline__ int roi_by_rank(const int* __restrict__ ctr, int R, int rank) {
@@ -216,6 +221,13 @@ __device__ __forceinline__ int roi_by_rank(const int* __restrict__ ctr, int R, i
     rank -= n;
   }
   return 0;   // unreachable when the buckets hold all R RoIs
+}
+
+}  // namespace jdet
+#include "roi_gather_tma.cuh"
+namespace jdet {
+__host__ __device__ inline int roi_table_layout_bytes(int nbins, int sampling_ratio) {
+  return g4::rec_layout(nbins, roi_table_fstride(sampling_ratio), 4 * sampling_ratio * sampling_ratio).max_bytes;
 }
 
 __device__ __forceinline__ void relayout_tile(const float* __restrict__ in, float* __restrict__ out, int C, int HW, int b,
@@ -279,8 +291,9 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
                                                             int W, int tiles_x, int tiles_y, const float* __restrict__ rois,
                                                             unsigned R, int PH, int PW, int sample_num,
                                                             unsigned char* __restrict__ tables, bool vec,
-                                                            int* __restrict__ work_counter, const __grid_constant__ RoiLevels L) {
-  extern __shared__ __align__(16) unsigned char smem[];
+                                                            int* __restrict__ work_counter, int pcap, int pxbytes,
+                                                            const __grid_constant__ RoiLevels L) {
+  extern __shared__ __align__(128) unsigned char smem[];
   if ((int)blockIdx.x < tiles_x) {
     const int b = tiles_y > 0 ? blockIdx.y / tiles_y : 0, ty = blockIdx.y - b * tiles_y;
     if (vec) relayout_tile_v4(in, nhwc, C, H * W, b, blockIdx.x * kTileW, ty * 32, reinterpret_cast<float(*)[kTileW + 1]>(smem));
@@ -311,16 +324,44 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
   }
   __syncthreads();
   const int level = s_level;
-  const int fstride = roi_table_fstride(sample_num);
-  int4* hdr = reinterpret_cast<int4*>(smem);                       // the record, in its final layout
-  int* cnt = reinterpret_cast<int*>(hdr + 1);
-  int2* fin = reinterpret_cast<int2*>(cnt + ((nbins + 3) & ~3));
-  int2* raw = fin + nbins * fstride;
-  if (threadIdx.x == 0) *hdr = make_int4(g.batch, __float_as_int(g.inv_count), fstride, level);
-  build_tap_table<VERSION>(g, nbins, PW, L.lv[level].H, L.lv[level].W, raw, fin, fstride, cnt, 4u * (unsigned)C);   // entries: BYTE offsets into one image of the channel-last map
-  const size_t stride = roi_table_stride(nbins, sample_num);
+  const int fstride = roi_table_fstride(sample_num), tpb = 4 * sample_num * sample_num;
+  const g4::RecLayout RL = g4::rec_layout(nbins, fstride, tpb);
+  int4* hdr = reinterpret_cast<int4*>(smem);                       // the record, in its final layout (roi_gather_tma.cuh)
+  int* cnt = reinterpret_cast<int*>(smem + RL.cnt_off);
+  int2* fin = reinterpret_cast<int2*>(smem + RL.fin_off);
+  int2* raw = reinterpret_cast<int2*>(smem + RL.max_bytes);
+  g4::ChunkScratch* scratch = reinterpret_cast<g4::ChunkScratch*>(raw + nbins * tpb);
+  if (threadIdx.x == 0) hdr[0] = make_int4(g.batch, __float_as_int(g.inv_count), fstride, level);
+  const int Hl = L.lv[level].H, Wl = L.lv[level].W;
+  if (pcap > 0) build_tap_table<VERSION, true>(g, nbins, PW, Hl, Wl, raw, fin, fstride, cnt);     // entries: ((y << 16) | x, weight)
+  else build_tap_table<VERSION, false>(g, nbins, PW, Hl, Wl, raw, fin, fstride, cnt, 4u * (unsigned)C);   // LSU path only: byte offsets at once
+  // One staged chunk (roi_gather_tma.cuh) when the RoI's distinct pixels fit pcap — guess first from the geometry, distinct
+  // pixels ~ area + 1.5 * (w + h) of the scaled box (cfg2 at 128 pixels: 3 wasted attempts, 15 missed of 2048) —, else the
+  // LSU-path record: entries become byte offsets into one image of the channel-last map.
+  const float rw = g.bin_w * (float)PW, rh = g.bin_h * (float)PH;
+  int bytes = RL.cnpx_off;
+  bool staged = false;
+  if (rw * rh + 1.5f * (rw + rh) + 2.f <= (float)pcap)
+    staged = g4::chunk_record(smem, nbins, fstride, tpb, pcap, pxbytes, Wl, g.batch * Hl * Wl, *scratch, &bytes);
+  if (!staged && pcap > 0) {
+    const unsigned px4c = 4u * (unsigned)C;
+    for (int e = threadIdx.x; e < nbins * fstride; e += blockDim.x) {
+      const int p = fin[e].x;
+      fin[e].x = (int)((unsigned)((p >> 16) * Wl + (p & 0xffff)) * px4c);
+    }
+  }
+  if (!staged) {
+    if (threadIdx.x == 0) hdr[1] = make_int4(0, 0, 0, bytes);
+    __syncthreads();
+  }
+  const size_t stride = (size_t)RL.max_bytes;
   int4* dst = reinterpret_cast<int4*>(tables + (size_t)idx * stride);
-  for (int i = threadIdx.x; i < (int)(stride / 16); i += blockDim.x) dst[i] = hdr[i];
+  for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = hdr[i];
+  if (threadIdx.x == 0) work_counter[64 + (size_t)(kRoiBuckets + 1) * R + idx] = bytes;
+  if (staged) {
+    if (threadIdx.x == 0) work_counter[64 + (size_t)kRoiBuckets * R + atomicAdd(work_counter + 2, 1)] = (int)idx;
+    return;
+  }
   if (threadIdx.x < 32) {   // cost = merged taps of the RoI -> its bucket of the gather's work queue (counters zeroed by the host side's memset)
     int taps = 0;
     for (int b = threadIdx.x; b < nbins; b += 32) taps += cnt[b];
@@ -334,7 +375,7 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
   }
 }
 
-// ---- gather kernel ------------------------------------------------------------------------------------
+// ---- LSU gather kernel: the RoIs the prologue did not stage (more distinct pixels than a chunk holds) ------------
 // grid = (R, C / SLAB), SLAB = 4*QL channels.  QL lanes span a bin's channels (QL = 32: one bin per warp, every
 // tap is 512 contiguous bytes of one channel-last pixel).  The CTA copies its RoI's table record (6.7 KB at
 // 7x7x2x2) into smem and then does nothing but loads and FMAs: bins are handed to warps through an smem counter
@@ -345,7 +386,7 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
 template <int QL, bool PAIR>
 __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __grid_constant__ RoiLevels L,
                                                              const unsigned char* __restrict__ tables, size_t stride, int C,
-                                                             int nbins, int nslabs, int items,
+                                                             int nbins, int nslabs, int R, uint32_t rec_bytes, int fin_off,
                                                              int* __restrict__ work_counter, float* __restrict__ out) {
   constexpr int SLAB = PAIR ? 8 * QL : 4 * QL;                      // PAIR: a lane owns two channel quads 4*QL apart
   extern __shared__ __align__(128) unsigned char smem[];
@@ -364,7 +405,10 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
   // NEXT item is fetched by a bulk-async copy while the current one is gathered, and the slab store of the
   // PREVIOUS item drains while the current one runs — a CTA never sits waiting for its 6.7 KB table or its store.
   int cur = blockIdx.x;                                            // first item: static; later ones from the counter
-  const int R = items / nslabs;
+  int items = 0;                                                   // RoIs the prologue left to this path = the LPT buckets
+#pragma unroll
+  for (int b = 0; b < kRoiBuckets; b++) items += work_counter[16 + b];
+  items *= nslabs;
   __shared__ int s_roi[2];                                         // RoI of the item whose table sits in rec buffer 0 / 1
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
@@ -373,8 +417,8 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
     if (cur < items) {
       const int roi = roi_by_rank(work_counter, R, cur / nslabs);
       s_roi[0] = roi;
-      mbar_expect_tx(&full[0], (uint32_t)stride);
-      bulk_g2s(rec_base, tables + (size_t)roi * stride, (uint32_t)stride, &full[0]);
+      mbar_expect_tx(&full[0], rec_bytes);
+      bulk_g2s(rec_base, tables + (size_t)roi * stride, rec_bytes, &full[0]);
     }
   }
   __syncthreads();
@@ -393,16 +437,16 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
       if (nx < items) {
         const int roi = roi_by_rank(work_counter, R, nx / nslabs);
         s_roi[buf ^ 1] = roi;                                      // (slot buf ^ 1 was last read before the barrier above)
-        mbar_expect_tx(&full[buf ^ 1], (uint32_t)stride);
-        bulk_g2s(rec_base + (buf ^ 1) * stride, tables + (size_t)roi * stride, (uint32_t)stride, &full[buf ^ 1]);
+        mbar_expect_tx(&full[buf ^ 1], rec_bytes);
+        bulk_g2s(rec_base + (buf ^ 1) * rec_bytes, tables + (size_t)roi * stride, rec_bytes, &full[buf ^ 1]);
       }
     }
     const int r = s_roi[buf], c0 = (cur % nslabs) * SLAB;
-    const int4* rec = reinterpret_cast<const int4*>(rec_base + buf * stride);
+    const int4* rec = reinterpret_cast<const int4*>(rec_base + buf * rec_bytes);
     const int batch = rec[0].x, fstride = rec[0].z;
     const float count = __int_as_float(rec[0].y);
-    const int* cnt = reinterpret_cast<const int*>(rec + 1);
-    const int2* fin = reinterpret_cast<const int2*>(cnt + ((nbins + 3) & ~3));
+    const int* cnt = reinterpret_cast<const int*>(rec + 2);        // record layout: roi_gather_tma.cuh (two header words, cnt, fin)
+    const int2* fin = reinterpret_cast<const int2*>(reinterpret_cast<const unsigned char*>(rec) + fin_off);
     const RoiLevel& lv = L.lv[rec[0].w];
     const float* base = lv.nhwc + (size_t)batch * lv.H * lv.W * C + c0 + 4 * q;
     const int icnt = (int)count;
@@ -447,9 +491,16 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
           asm volatile("" : "+f"(v[j].x), "+f"(v[j].y), "+f"(v[j].z), "+f"(v[j].w));
         const float w0 = __int_as_float(t01.y), w1 = __int_as_float(t01.w);   // 0 on padding
         const float w2 = __int_as_float(t23.y), w3 = __int_as_float(t23.w);
-#define JDET_ACC(a, c, i0) a.c = fmaf(w3, v[i0 + 6].c, fmaf(w2, v[i0 + 4].c, fmaf(w1, v[i0 + 2].c, fmaf(w0, v[i0].c, a.c))))
-        JDET_ACC(acc0, x, 0); JDET_ACC(acc0, y, 0); JDET_ACC(acc0, z, 0); JDET_ACC(acc0, w, 0);
-        JDET_ACC(acc1, x, 1); JDET_ACC(acc1, y, 1); JDET_ACC(acc1, z, 1); JDET_ACC(acc1, w, 1);
+        // packed FFMA2: same fma chain per component (tap 0, 1, 2, 3), two components per issue slot
+#define JDET_ACC(a, i0)                                                                                                \
+  do {                                                                                                                 \
+    g4::fma2(a.x, a.y, w0, v[i0].x, v[i0].y);         g4::fma2(a.z, a.w, w0, v[i0].z, v[i0].w);                         \
+    g4::fma2(a.x, a.y, w1, v[i0 + 2].x, v[i0 + 2].y); g4::fma2(a.z, a.w, w1, v[i0 + 2].z, v[i0 + 2].w);                 \
+    g4::fma2(a.x, a.y, w2, v[i0 + 4].x, v[i0 + 4].y); g4::fma2(a.z, a.w, w2, v[i0 + 4].z, v[i0 + 4].w);                 \
+    g4::fma2(a.x, a.y, w3, v[i0 + 6].x, v[i0 + 6].y); g4::fma2(a.z, a.w, w3, v[i0 + 6].z, v[i0 + 6].w);                 \
+  } while (0)
+        JDET_ACC(acc0, 0);
+        JDET_ACC(acc1, 1);
 #undef JDET_ACC
       }
       if (valid) {
@@ -570,6 +621,7 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
   if (threadIdx.x == 0) bulk_s2g_wait_read();                      // smem must outlive the last store's read
 }
 
+
 // ---- direct NCHW kernel --------------------------------------------------------------------------
 // grid = (R, channel chunks); thread task = (channel, bin); taps from the per-RoI table when it fits,
 // otherwise recomputed per element (adaptive sampling grids of huge RoIs).
@@ -577,7 +629,7 @@ template <int VERSION>
 __global__ void __launch_bounds__(256) roi_align_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
                                                               int C, int H, int W, int PH, int PW, float spatial_scale,
                                                               int sample_num, int ch_per_cta, float* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   const int nbins = PH * PW;
   const int r = blockIdx.x, c0 = blockIdx.y * ch_per_cta;
   const int c1 = min(C, c0 + ch_per_cta);
@@ -633,7 +685,7 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nhwc_kernel(const float* __
                                                                   const float* __restrict__ rois, int C, int H, int W,
                                                                   int PH, int PW, float spatial_scale, int sample_num,
                                                                   float* __restrict__ grad_nhwc) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   const int nbins = PH * PW;
   const int r = blockIdx.x, c0 = blockIdx.y * SLAB;
   constexpr int QL = SLAB / 4;
@@ -671,7 +723,7 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nchw_kernel(const float* __
                                                                   const float* __restrict__ rois, int C, int H, int W,
                                                                   int PH, int PW, float spatial_scale, int sample_num,
                                                                   int ch_per_cta, float* __restrict__ grad_in) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   const int nbins = PH * PW;
   const int r = blockIdx.x, c0 = blockIdx.y * ch_per_cta;
   const int c1 = min(C, c0 + ch_per_cta);
@@ -707,11 +759,66 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nchw_kernel(const float* __
   }
 }
 
+// ---- configuration of the staged path (roi_gather_tma.cuh) ------------------------------------------------------
+// slab = channels staged per pixel (128, or 64 when C % 128 != 0); ring = bytes of the staging ring, the largest
+// power of two that leaves room for two output slabs and three table records in the 227 KB of an SM; pcap = the most
+// pixels a whole-RoI chunk may hold (a quarter of the ring: chunks must be small against the ring, see roi_gather_tma.cuh).  ok == false: the shape does not fit (huge pooled grids) -> direct kernel.
+struct StagedCfg { bool ok; int slab, pxbytes, pcap; unsigned ring; size_t smem, stride; };
+// The TMA-staged gather (roi_gather_tma.cuh) is opt-in: JDET_ROI_TMA=1.  Measured on B200 (profiles/r02_roi_tma_*.txt,
+// DESIGN.md section 4.3): it loses to the L1-path kernel on cfg2 — 46 us for the 1244 small RoIs it stages against ~30 us —
+// so by default every RoI takes the LSU path; the staged path stays parity-tested (tests/test_gpu_parity.py).
+static bool roi_tma_enabled() { const char* e = getenv("JDET_ROI_TMA"); return e && e[0] == '1'; }
+static StagedCfg staged_cfg(int C, int PH, int PW, int sample_num) {
+  StagedCfg c{};
+  if (sample_num <= 0 || C % 64 != 0 || C > 64 * g4::kMaxSlabs) return c;
+  const long long nbins_ll = (long long)PH * PW;
+  if (nbins_ll * sample_num * sample_num > kMaxSamples) return c;
+  const int nbins = (int)nbins_ll, tpb = 4 * sample_num * sample_num;
+  c.slab = (C % 128 == 0) ? 128 : 64;
+  c.pxbytes = c.slab * 4;
+  c.stride = roi_table_stride(nbins, sample_num);
+  const size_t fixed = 2 * ((((size_t)c.slab * (nbins | 1) + 3) & ~(size_t)3) * 4) + g4::kTB * c.stride + 2560;   // + the kernel's static shared memory
+  for (unsigned ring = 128u << 10; ring >= (32u << 10); ring >>= 1) {
+    if (fixed + ring > 227u * 1024) continue;
+    const int pcap = (int)(ring / 2 / c.pxbytes);       // a staged RoI is one chunk of at most half the ring
+    if ((int)(ring / 2 / c.pxbytes) < ((tpb + 3) & ~3)) break;   // one bin must always fit a chunk
+    c.ok = true; c.ring = ring; c.pcap = pcap; c.smem = fixed - 2560 + ring;
+    break;
+  }
+  return c;
+}
+
 static bool use_staged(int B, int C, int H, int W, int R, int PH, int PW, int sample_num) {
-  if (sample_num <= 0 || C % 64 != 0) return false;
-  if ((long long)PH * PW * sample_num * sample_num > kMaxSamples) return false;
+  if (!staged_cfg(C, PH, PW, sample_num).ok) return false;
+  if (H >= 32768 || W >= 32768 || (long long)B * H * W >= (1ll << 31)) return false;   // packed (y, x) taps, 32-bit gather rows
   // re-laying the map moves 8*B*C*H*W bytes; it pays once the RoI set samples the map densely
   return (long long)R * PH * PW * sample_num * sample_num * 8 >= (long long)B * H * W;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+    return (TensorMapEncodeFn)p;
+  }();
+  return fn;
+}
+// (B*H*W, C) fp32 view of a channel-last map; one gather row = one pixel, box = {slab channels, 1 row}
+static cudaError_t make_pixel_map(CUtensorMap* map, const float* nhwc, long long pixels, int C, int slab) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return cudaErrorNotSupported;
+  cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)pixels};
+  cuuint64_t gstr[1] = {(cuuint64_t)C * 4};
+  cuuint32_t box[2] = {(cuuint32_t)slab, 1};
+  cuuint32_t es[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(nhwc), gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 // one prologue launch: re-layout of ONE NCHW map (input_nchw may be null) and, if with_tables, the tap tables of all RoIs
@@ -719,55 +826,83 @@ static cudaError_t launch_prologue(int version, const float* input_nchw, float* 
                                    bool with_tables, unsigned char* tables, int* work_counter, const float* rois, int R, int PH,
                                    int PW, int sampling_ratio, const RoiLevels& L, cudaStream_t st) {
   const int nbins = PH * PW;
-  const size_t stride = roi_table_stride(nbins, sampling_ratio);
+  const StagedCfg cfg = staged_cfg(C, PH, PW, sampling_ratio);
+  if (!cfg.ok) return cudaErrorInvalidConfiguration;
   const int Rt = with_tables ? R : 0;
-  for (int l = 0; l < L.n; l++)   // table entries are 32-bit byte offsets into one image of the channel-last map
+  for (int l = 0; l < L.n; l++) {  // taps are packed (y << 16) | x; gather rows are 32-bit pixel indices, LSU entries 32-bit byte offsets
     if ((unsigned long long)L.lv[l].H * L.lv[l].W * C >= (1ull << 30)) return cudaErrorInvalidConfiguration;
+    if (L.lv[l].H >= 32768 || L.lv[l].W >= 32768 || (long long)B * L.lv[l].H * L.lv[l].W >= (1ll << 31)) return cudaErrorInvalidConfiguration;
+  }
   const bool vec = input_nchw && ((H * W) & 3) == 0 && (C & 3) == 0 && ((((uintptr_t)input_nchw) | ((uintptr_t)nhwc_scratch)) & 15) == 0;
   const int tiles_x = input_nchw ? jdet_ceil_div(H * W, vec ? kTileW : 32) : 0, tiles_y = input_nchw ? jdet_ceil_div(C, 32) : 0;
   const int rows = input_nchw ? tiles_y * B : jdet_ceil_div(Rt, 1024);
   if (rows > 65535) return cudaErrorInvalidConfiguration;
   if (rows == 0) return cudaSuccess;
   dim3 pgrid(tiles_x + jdet_ceil_div(Rt, rows), rows);
-  const size_t smem = std::max(stride + (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2), sizeof(float) * 32 * (kTileW + 1));
+  const size_t smem = std::max(cfg.stride + (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2) + sizeof(g4::ChunkScratch) + 16,
+                               sizeof(float) * 32 * (kTileW + 1));
   if (version == 1) {
     if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-    roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, L);
+    roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, roi_tma_enabled() ? cfg.pcap : 0, cfg.pxbytes, L);
   } else {
     if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-    roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, L);
+    roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, roi_tma_enabled() ? cfg.pcap : 0, cfg.pxbytes, L);
   }
   return cudaGetLastError();
 }
 
-static cudaError_t launch_gather(const RoiLevels& L, const unsigned char* tables, int* work_counter, int C, int R, int PH, int PW,
+// two gather launches over the tables of one prologue: the TMA-staged RoIs, then the rest on the LSU path.  Both read their
+// work lists (and how many RoIs they hold) from device memory; a launch without work exits at once.
+static cudaError_t launch_gather(const RoiLevels& L, int B, const unsigned char* tables, int* work_counter, int C, int R, int PH, int PW,
                                  int sampling_ratio, float* output, cudaStream_t st) {
   const int nbins = PH * PW;
-  const size_t stride = roi_table_stride(nbins, sampling_ratio);
-  const int slab = (C % 128 == 0) ? 128 : 64;
-  const size_t smem = (((size_t)slab * (nbins | 1) + 3) & ~(size_t)3) * 4 + 2 * stride;
-  const int nslabs = C / slab;
-  const long long items_ll = (long long)R * nslabs;
-  if (items_ll > 0x7fffffffLL - 148 * 8) return cudaErrorInvalidConfiguration;
-  const int items = (int)items_ll;
+  const StagedCfg cfg = staged_cfg(C, PH, PW, sampling_ratio);
+  if (!cfg.ok) return cudaErrorInvalidConfiguration;
+  const int nslabs = C / cfg.slab;
+  if (nslabs > g4::kMaxSlabs) return cudaErrorInvalidConfiguration;
+  if ((long long)R * nslabs > 0x7fffffffLL - 148 * 8) return cudaErrorInvalidConfiguration;
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const bool pair = slab == 128;   // two bins per warp (A/B on one box, cfg2 whole op: 116.8 vs 122.1 us)
-  // (warps per CTA, pair mode, 7x7 = 25 warp-tasks per item, A/B on one B200, whole op: 8 warps x 3 CTAs/SM 115.7 us,
-  //  6 x 4: 115.7, 5 x 5 (no idle task slot in the last round): 119.8 — the end-of-item barrier is not what binds it;
-  //  one-bin-per-warp form, 7 warps with round-robin bins: 124-127 vs 121 for 8 warps + smem counter)
-  const int threads = 256;
-  const int grid = (int)std::min<long long>(items_ll, (long long)sms * (pair ? 3 : 4));
-  // (measured on B200, cfg2, gather only: 16 taps per bin straight from per-CTA tables 106 us; taps merged per bin
-  //  95 us; tables moved to the prologue, no other change 90 us; 8 loads per step actually in flight (see the
-  //  launch bounds) and lean steps 71 us; persistent CTAs with table prefetch: see profiles/)
+  const int fstride = roi_table_fstride(sampling_ratio), tpb = 4 * sampling_ratio * sampling_ratio;
+  const g4::RecLayout RL = g4::rec_layout(nbins, fstride, tpb);
+  // ---- staged RoIs: cp.async.bulk.tensor gather4 into the ring, gather from shared memory
+  if (roi_tma_enabled()) {
+  g4::GatherMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int l = 0; l < L.n; l++) {
+    cudaError_t e = make_pixel_map(&maps.map[l], L.lv[l].nhwc, (long long)B * L.lv[l].H * L.lv[l].W, C, cfg.slab);
+    if (e != cudaSuccess) return e;
+  }
+  g4::GatherArgs a{};
+  a.tables = tables; a.rec_bytes = work_counter + 64 + (size_t)(kRoiBuckets + 1) * R; a.stride = cfg.stride;
+  a.work_counter = work_counter; a.out = output;
+  a.C = C; a.nbins = nbins; a.nslabs = nslabs; a.items = R;
+  a.fstride = fstride; a.tpb = tpb;
+  a.ring = cfg.ring;
+#ifdef JDET_G4_STATS
+  a.stats = g_jdet_g4_stats;
+#endif
+  const int grid = std::min(R, sms);
+  if (cfg.slab == 128) {
+    cudaError_t e_ = cudaFuncSetAttribute(g4::roi_gather4_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem); if (e_ != cudaSuccess) return e_;
+    g4::roi_gather4_kernel<128><<<grid, g4::kThreads, cfg.smem, st>>>(maps, a);
+  } else {
+    cudaError_t e_ = cudaFuncSetAttribute(g4::roi_gather4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem); if (e_ != cudaSuccess) return e_;
+    g4::roi_gather4_kernel<64><<<grid, g4::kThreads, cfg.smem, st>>>(maps, a);
+  }
+  { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; }
+  }
+  // ---- the other RoIs: L1-path gathers straight from the channel-last map (round-1 kernel, now with packed FFMA2)
+  const uint32_t rec_bytes = (uint32_t)RL.cnpx_off;                  // header, cnt, fin
+  const size_t smem = (((size_t)cfg.slab * (nbins | 1) + 3) & ~(size_t)3) * 4 + 2 * (size_t)rec_bytes;
+  const bool pair = cfg.slab == 128;   // two bins per warp (A/B on one box, cfg2 whole op: 116.8 vs 122.1 us)
+  const int lgrid = (int)std::min<long long>((long long)R * nslabs, (long long)sms * (pair ? 3 : 4));
 #define JDET_LAUNCH_ROI(QL_, PAIR_)                                                                                    \
   do {                                                                                                                 \
     if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_gather_kernel<QL_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; } \
-    roi_gather_kernel<QL_, PAIR_><<<grid, threads, smem, st>>>(L, tables, stride, C, nbins, nslabs, items, work_counter, output); \
+    roi_gather_kernel<QL_, PAIR_><<<lgrid, 256, smem, st>>>(L, tables, cfg.stride, C, nbins, nslabs, R, rec_bytes, RL.fin_off, work_counter, output); \
   } while (0)
-  if (slab == 128) { if (pair) JDET_LAUNCH_ROI(16, true); else JDET_LAUNCH_ROI(32, false); }
-  else JDET_LAUNCH_ROI(16, false);
+  if (pair) JDET_LAUNCH_ROI(16, true); else JDET_LAUNCH_ROI(16, false);
 #undef JDET_LAUNCH_ROI
   return cudaGetLastError();
 }
@@ -785,7 +920,7 @@ static cudaError_t launch_staged(int version, const float* input_nchw, const flo
   cudaError_t e = launch_prologue(version, input_nchw, nhwc_scratch, B, C, H, W, true, tables, work_counter, rois, R, PH, PW,
                                   sampling_ratio, L, st);
   if (e != cudaSuccess) return e;
-  return launch_gather(L, tables, work_counter, C, R, PH, PW, sampling_ratio, output, st);
+  return launch_gather(L, B, tables, work_counter, C, R, PH, PW, sampling_ratio, output, st);
 }
 
 }  // namespace jdet
@@ -842,8 +977,7 @@ JDET_API int jdet_roi_align_rotated_nhwc(int version, const float* input_nhwc, i
     return JDET_ERR_BAD_ARG;
   if (R == 0 || C == 0) return 0;
   if (!input_nhwc || !rois || !output || B == 0 || H == 0 || W == 0) return JDET_ERR_BAD_ARG;
-  if (sampling_ratio <= 0 || C % 64 != 0 || (long long)PH * PW * sampling_ratio * sampling_ratio > kMaxSamples)
-    return JDET_ERR_UNSUPPORTED;
+  if (!staged_cfg(C, PH, PW, sampling_ratio).ok) return JDET_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < jdet_roi_align_rotated_nhwc_workspace_bytes(R, PH, PW, sampling_ratio))
     return JDET_ERR_WORKSPACE;
   return (int)launch_staged(version, nullptr, input_nhwc, nullptr, (unsigned char*)workspace, rois, B, C, H, W, R, PH, PW,
@@ -872,8 +1006,7 @@ JDET_API int jdet_roi_align_rotated_fpn(int version, const float* const* feats, 
     return JDET_ERR_BAD_ARG;
   if (R == 0) return 0;
   if (!rois || !output) return JDET_ERR_BAD_ARG;
-  if (sampling_ratio <= 0 || C % 64 != 0 || (long long)PH * PW * sampling_ratio * sampling_ratio > kMaxSamples)
-    return JDET_ERR_UNSUPPORTED;
+  if (!staged_cfg(C, PH, PW, sampling_ratio).ok) return JDET_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < jdet_roi_align_rotated_fpn_workspace_bytes(nlevels, B, C, Hs, Ws, R, PH, PW, sampling_ratio))
     return JDET_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -891,7 +1024,7 @@ JDET_API int jdet_roi_align_rotated_fpn(int version, const float* const* feats, 
   for (int l = 0; l < nlevels; l++)
     JDET_RETURN_IF_CUDA(launch_prologue(version, feats[l], const_cast<float*>(L.lv[l].nhwc), B, C, Hs[l], Ws[l], l == 0, tables,
                                         work_counter, rois, R, PH, PW, sampling_ratio, L, st));
-  JDET_RETURN_IF_CUDA(launch_gather(L, tables, work_counter, C, R, PH, PW, sampling_ratio, output, st));
+  JDET_RETURN_IF_CUDA(launch_gather(L, B, tables, work_counter, C, R, PH, PW, sampling_ratio, output, st));
   return 0;
 }
 

@@ -341,6 +341,32 @@ def test_roi_align_module_and_reference_selftest_shape():
         assert layer.execute(cu(x), cu(rois)).shape == (2, 1024, 7, 7)
 
 
+@pytest.mark.parametrize("shape", [dict(B=2, C=256, H=48, W=64, R=600, out=(7, 7), sr=2, scale=0.25),
+                                   dict(B=1, C=64, H=40, W=40, R=300, out=(6, 6), sr=2, scale=0.125),
+                                   dict(B=2, C=128, H=32, W=32, R=200, out=(5, 3), sr=3, scale=0.125)])
+def test_roi_align_tma_staged_path(shape, monkeypatch):
+    """JDET_ROI_TMA=1: small RoIs go through the tensor-map gather4 staging kernel (roi_gather_tma.cuh), the rest through
+    the LSU kernel.  Same numbers as the default path bit for bit (same taps, same order of the per-bin sums)."""
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((shape["B"], shape["C"], shape["H"], shape["W"])).astype(np.float32)
+    extent = shape["W"] / shape["scale"]
+    rois = _rois(rng, shape["R"], shape["B"], extent, 4, extent / 3)
+    rois[:4, 1:3] = [[-40, -40], [extent + 30, 5], [0, 0], [extent, extent]]          # outside / on the border
+    for version, mod in ((1, ops().roi_align_rotated_v1), (0, ops().roi_align_rotated)):
+        monkeypatch.delenv("JDET_ROI_TMA", raising=False)
+        base = mod.roi_align(cu(x), cu(rois), shape["out"], shape["scale"], shape["sr"]).cpu().numpy()
+        monkeypatch.setenv("JDET_ROI_TMA", "1")
+        got = mod.roi_align(cu(x), cu(rois), shape["out"], shape["scale"], shape["sr"]).cpu().numpy()
+        want = oracle.roi_align_rotated(x, rois, shape["out"], shape["scale"], shape["sr"], version)
+        assert np.abs(got - want).max() <= TOL
+        assert np.array_equal(bits(got), bits(base))
+
+
+def test_roi_align_full_size_cfg2_tma_staged(monkeypatch):
+    monkeypatch.setenv("JDET_ROI_TMA", "1")
+    test_roi_align_full_size_cfg2()
+
+
 def test_roi_align_full_size_cfg2():
     """BASELINE cfg2: 256-ch 256x256 map, 2048 RoIs, 7x7, sampling 2 — whole output vs the oracle."""
     rng = np.random.default_rng(0)
