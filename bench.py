@@ -267,9 +267,7 @@ def run_ours(args):
     line = {"metric": "rotated RoIs/s", "value": value, "unit": "RoIs/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "roi_align_rotated_v1: 256-ch 256x256 FPN map, 2048 RoIs, 7x7 output, sampling_ratio 2, "
-                                   "spatial_scale 0.25 (BASELINE configs[1]); one tile per GPU",
-                       "rois_per_gpu": n_rois, "l2": "256 MiB memset + 256 MiB read between timed steps (outside the events): L2 holds no input and no dirty line",
+            "config": {"workload": WORKLOAD, "rois_per_gpu": n_rois, "l2": "256 MiB memset + 256 MiB read between timed steps (outside the events): L2 holds no input and no dirty line",
                        "timing": "CUDA events per step on the launch stream, max over ranks",
                        "prewarm_s": PREWARM_S},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": 2 * K, "roofline": roofline}
@@ -277,9 +275,18 @@ def run_ours(args):
     extra = {}
     if not args.no_extra:
         extra = run_extra(torch, dist if world > 1 else None, ops, jdist, dev, rank, world, peaks, flush)
-    line["extra"] = extra
+        if rank == 0 and world == 1:
+            extra["reference_cuda"] = reference_cuda_legs(torch, dev, flush, ms_per_step, extra)
+    # compact table of every other leg, inside `config` (the driver's record keeps `config` whole but only the key names of
+    # `extra`): leg -> [value, unit, ms_per_step, roofline frac]; reference_cuda: leg -> [reference kernel ms, ours ms, ratio]
+    line["config"]["legs"] = {k: [float("%.6g" % v["value"]), v["unit"], round(v["ms_per_step"], 4), round(v["roofline"]["frac"], 4)]
+                              for k, v in extra.items() if isinstance(v, dict) and "roofline" in v}
+    if "reference_cuda" in extra:
+        line["config"]["legs_vs_reference_cuda_kernels"] = {k: [round(v["reference_ms"], 4), round(v["ours_ms"], 4), round(v["ratio"], 2)]
+                                                            for k, v in extra["reference_cuda"].items() if isinstance(v, dict)}
     if rank == 0 and world == 1 and not args.no_extra:
         line["cpu_baseline"] = cpu_baseline_roi(feat.cpu().numpy(), rois_h)
+    line["extra"] = extra
     if rank == 0:
         emit(line)
     if world > 1:
@@ -462,13 +469,123 @@ def run_extra(torch, dist, ops, jdist, dev, rank, world, peaks, flush):
     K = 5
     ms = agg(time_steps(torch, fn, K, 3, flush)) / K
     flops = 2.0 * 256 * 2304 * sum(x.shape[0] * x.shape[2] * x.shape[3] for x in xs)
+    tf32 = measure_tf32_peak(torch, dev)
+    ach = flops / (ms * 1e-3) / 1e12
     ex["align_conv"] = {"metric": "positions/s", "value": sum(x.shape[0] * x.shape[2] * x.shape[3] for x in xs) * world / (ms * 1e-3),
                         "unit": "positions/s", "ms_per_step": ms, "steps": K,
                         "config": {"workload": "AlignConv 256->256 3x3, bs 8 x {128,64,32,16,8}^2 (BASELINE configs[3])"},
-                        "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"],
-                                     "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "flops": flops,
-                                     "note": "peak is the measured bf16 cuBLAS figure; the kernel computes fp32-class results"}}
+                        "roofline": {"bound": "tensor", "achieved": ach, "peak": tf32 / 3.0, "unit": "TFLOP/s", "frac": ach / (tf32 / 3.0),
+                                     "flops": flops, "tf32_tflops_measured": tf32, "tensor_tflops_issued": 3.0 * ach,
+                                     "note": "achieved = fp32-equivalent FLOPs of the convolution; the kernel issues 3 TF32 MMAs per "
+                                             "product (hi*hi + hi*lo + lo*hi, fp32-class accuracy as the reference's SGEMM), so the "
+                                             "ceiling is a third of the TF32 rate, measured in this run: torch.matmul 8192^3 with "
+                                             "allow_tf32, best of 5"}}
     return ex
+
+
+def measure_tf32_peak(torch, dev):
+    """cuBLAS TF32 GEMM rate on this GPU, in this run (the driver's MEASURED_PEAKS.json has no TF32 figure)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn((n, n), device=dev), torch.randn((n, n), device=dev)
+        best = 1e9
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def reference_cuda_legs(torch, dev, flush, roi_ms, extra):
+    """the three CUDA-only ops have no reference CPU path — their baseline is the reference's OWN CUDA kernel
+    (source strings compiled for sm_100a into oracle/_ref/libref_cuda.so, reference launch geometry) on the same GPU, same
+    inputs, same CUDA events and L2 flush.  A reported baseline (rank 0, N = 1); never part of the product path."""
+    out = {}
+    try:
+        import _refcuda
+        from _inputs import clustered_boxes, dota_boxes, s2anet_anchors, tie_free_scores
+        if not _refcuda.available():
+            return {"note": "oracle/_ref/libref_cuda.so did not travel"}
+        import ctypes
+        import oracle
+        R = oracle.ref_cuda()
+        rng = np.random.default_rng(100)
+        cu = lambda a, dt=torch.float32: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
+        st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        pp = lambda t: ctypes.c_void_p(t.data_ptr())
+        f32 = lambda v: ctypes.c_float(np.float32(v))
+
+        def leg(name, fn, K, ours_ms, what):
+            fn()
+            ms = time_steps(torch, fn, K, 2, flush) / K
+            out[name] = {"reference_ms": ms, "ours_ms": ours_ms, "ratio": ms / ours_ms, "what": what}
+
+        # RoIAlign cfg2
+        g = torch.Generator(device=dev).manual_seed(1234)
+        feat = torch.randn((1, 256, 256, 256), device=dev, generator=g)
+        rois = cu(make_cfg2(0))
+        o = torch.empty((2048, 256, 7, 7), device=dev)
+        leg("roi_align_rotated", lambda: R.ref_roi_align_rotated_cuda(1, pp(feat), pp(rois), 2048, 256, 256, 256, 7, 7, f32(0.25), ctypes.c_float(2.0), pp(o), st()),
+            20, roi_ms, "ROIAlignRotatedForward v1 (ops/roi_align_rotated_v1.py:70-147), cfg2")
+        del feat, o
+        # IoU 16k^2 and 1k^2
+        for nn, K in ((16384, 3), (1000, 20)):
+            b1, b2 = cu(dota_boxes(rng, nn)), cu(dota_boxes(rng, nn))
+            o = torch.empty((nn, nn), device=dev)
+            key = "box_iou_rotated_%dk" % (nn // 1000)
+            leg(key, lambda: R.ref_box_iou_rotated_cuda(pp(b1), nn, pp(b2), nn, pp(o), st()), K, extra[key]["ms_per_step"],
+                "box_iou_rotated_cuda_kernel (ops/box_iou_rotated.py:412-461), %dx%d" % (nn, nn))
+            del b1, b2, o
+        # feature_refine level 0 of cfg4 would need its own ours-leg; use the whole cfg4 (5 levels) like the ours-leg
+        levels = [(128, 8), (64, 16), (32, 32), (16, 64), (8, 128)]
+        g = torch.Generator(device=dev).manual_seed(77)
+        xs = [torch.randn((8, 256, hw, hw), device=dev, generator=g) for hw, _ in levels]
+        bx = [cu(s2anet_anchors(rng, 8, hw, hw, s_))[..., [1, 0, 2, 3, 4]].contiguous() for hw, s_ in levels]
+        os_ = [torch.empty_like(x) for x in xs]
+        for points in (1, 5):
+            leg("feature_refine_p%d" % points,
+                lambda: [R.ref_feature_refine_cuda(pp(x), pp(b), 8, 256, x.shape[2], x.shape[3], points, f32(1.0 / s_), pp(o_), st())
+                         for x, b, o_, (_, s_) in zip(xs, bx, os_, levels)],
+                5, extra["feature_refine_p%d" % points]["ms_per_step"], "feature_refine_forward_kernel (ops/fr.py:114-165), cfg4, 5 levels")
+        del os_, bx
+        # AlignConv: reference = ~25 elementwise offset kernels (not timed) + deformable_im2col + SGEMM per level
+        an = [cu(s2anet_anchors(rng, 8, hw, hw, s_)) for hw, s_ in levels]
+        from jdet_b200.models.roi_heads.s2anet_head import AlignConv
+        acm = AlignConv(256, 256, 3)
+        offs = [acm.get_offset_batched(a, s_) for a, (_, s_) in zip(an, levels)]
+        w = torch.randn((256, 2304), device=dev) * 0.02
+        cols = [torch.empty((2304, 8 * hw * hw), device=dev) for hw, _ in levels]
+
+        def ref_ac():
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            for x, of, col in zip(xs, offs, cols):
+                H = x.shape[2]
+                R.ref_deformable_im2col_cuda(pp(x), pp(of), 256, H, H, 3, 3, 1, 1, 1, 1, 1, 1, 8, 1, pp(col), st())
+                torch.matmul(w, col)
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        leg("align_conv", ref_ac, 3, extra["align_conv"]["ms_per_step"],
+            "deformable_im2col_gpu_kernel (ops/dcn_v1.py:131-184) + fp32 SGEMM (torch.matmul, TF32 off) per level; the reference's "
+            "offset micro-kernels are not included")
+        del xs, an, offs, cols
+        # NMS: the reference mask kernel alone (its host-side greedy pass over a 1.25 GB managed mask is not timed)
+        n = 100000
+        d = np.concatenate([clustered_boxes(rng, n // 2, 50), dota_boxes(rng, n - n // 2)])
+        s_, l_ = tie_free_scores(rng, n), rng.integers(0, 15, n)
+        d6 = cu(np.concatenate([d, l_[:, None].astype(np.float32)], 1))
+        order = torch.argsort(cu(s_), descending=True).int()
+        keep, ms = _refcuda.nms_rotated_keep(d6, order, 0.1)
+        out["nms_rotated"] = {"reference_ms": float(ms), "ours_ms": extra["nms_rotated"]["ms_per_step"],
+                              "ratio": float(ms) / extra["nms_rotated"]["ms_per_step"],
+                              "what": "nms_rotated_cuda_kernel alone (ops/nms_rotated.py:352-411), 100k x 15, one launch; the "
+                                      "reference then reduces a 1.25 GB mask on the host, which is not in this number"}
+    except Exception as e:  # a reported baseline, never a reason to fail the bench
+        out["note"] = "reference CUDA legs incomplete: %r" % (e,)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -520,36 +637,37 @@ def cpu_baseline_roi(feat_np, rois_np, budget_s=12.0):
     return out
 
 
+WORKLOAD = ("roi_align_rotated_v1: 256-ch 256x256 FPN map, 2048 RoIs, 7x7 output, sampling_ratio 2, "
+            "spatial_scale 0.25 (BASELINE configs[1]); one tile per GPU")
+
+
 def run_reference(args):
-    """--impl reference: the CPU implementation of the headline path on the host cores."""
+    """--impl reference: the CPU implementation of the headline path on ALL host cores, the full 2048 RoIs per step."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    ncpu = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)          # torchrun exports OMP_NUM_THREADS=1: this arm must use every core
     import oracle
     rng = np.random.default_rng(1234)
     feat = rng.standard_normal((1, 256, 256, 256)).astype(np.float32)
     rois = make_cfg2(0)
-    sample = 256
-    K, W = args.steps, args.warmup
-    K = min(K, 40)
-    for _ in range(min(W, 3)):
-        oracle.roi_align_rotated(feat, rois[:sample], (7, 7), 0.25, 2, 1)
+    K, W = min(args.steps, 40), min(args.warmup, 3)
+    for _ in range(W):
+        oracle.roi_align_rotated(feat, rois, (7, 7), 0.25, 2, 1, threads=ncpu)
     t0 = time.perf_counter()
     for k in range(K):
-        lo = (k * sample) % 2048
-        oracle.roi_align_rotated(feat, rois[lo:lo + sample], (7, 7), 0.25, 2, 1)
+        oracle.roi_align_rotated(feat, rois, (7, 7), 0.25, 2, 1, threads=ncpu)
     dt = time.perf_counter() - t0
-    v = sample * K / dt
-    cores = oracle.max_threads()
+    v = rois.shape[0] * K / dt
     line = {"impl": "reference", "metric": "rotated RoIs/s", "value": v, "unit": "RoIs/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "roi_align_rotated_v1: 256-ch 256x256 FPN map, 2048 RoIs, 7x7 output, sampling_ratio 2, "
-                                   "spatial_scale 0.25 (BASELINE configs[1]); each step = %d of the 2048 RoIs" % sample},
-            "cpu_baseline": {"value": v, "unit": "RoIs/s", "cores": cores, "kind": "port",
-                             "sample": "%d RoIs per step x %d steps; the reference has no CPU path for roi_align_rotated "
-                                       "(CUDA-only), so this is oracle/oracle.cpp (OpenMP over RoIs)" % (sample, K)},
+            "config": {"workload": WORKLOAD, "rois_per_gpu": int(rois.shape[0])},
+            "cpu_baseline": {"value": v, "unit": "RoIs/s", "cores": ncpu, "kind": "port",
+                             "sample": "all 2048 RoIs per step x %d steps on %d threads; the reference has no CPU path for "
+                                       "roi_align_rotated (CUDA-only), so this is oracle/oracle.cpp (OpenMP over RoIs)" % (K, ncpu)},
             "e2e": {"value": v, "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
