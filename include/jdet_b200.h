@@ -65,6 +65,23 @@ size_t jdet_argsort_desc_workspace_bytes(int n);
 int jdet_argsort_desc(const float* scores, int n, int* order, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* ---- tile -> image merge NMS over quadrilaterals -------------------------------------------------
+ * replaces: py_cpu_nms_poly_fast / py_cpu_nms_poly data/devkits/result_merge.py:69-131, :33-66 (Python loops around
+ *           iou_poly, ops/nms_poly.py:247-252 = shapely polygon intersection; restated for convex quadrilaterals in binary64).
+ * dets (n, 9) = 4 corner points + score; order (n,) from jdet_argsort_desc(scores); keep (n,) bytes at original indices.
+ * fast != 0: the bounding-box pre-filter of the _fast variant.  Suppresses on iou > iou_threshold (a double, >= 0).       */
+size_t jdet_nms_poly_workspace_bytes(int n);
+int jdet_nms_poly(const float* dets, int n, const int* order, double iou_threshold, int fast, unsigned char* keep,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* fixed-size detection record for the end-of-step all-gather: rows [x,y,w,h,theta,score,label] of the kept
+ * boxes in descending score order, zero padded to max_per_img rows, + a last row holding the count — what the tail of
+ * multiclass_nms_rotated (ops/nms_rotated.py:584-596: re-sort by score, [:max_num]) leaves per image.  One launch, written
+ * straight into the caller's send buffer.  dets (n, box_length) [label in column 5 when box_length == 6]; order (n,) from
+ * jdet_argsort_desc(scores); keep (n,) bytes from jdet_nms_rotated; record (max_per_img + 1, 7) fp32, fully written.       */
+int jdet_pack_detections(const float* dets, int n, int box_length, const float* scores, const int* order,
+                         const unsigned char* keep, int max_per_img, float* record, void* stream);
+
 /* ---- roi_align_rotated -----------------------------------------------------------------------
  * replaces: version 1: _RotatedROIAlign_v1.execute ops/roi_align_rotated_v1.py:300-326 (kernel :70-147)
  *           version 0: _RotatedROIAlign.execute    ops/roi_align_rotated.py:257-283   (kernel :60-127)

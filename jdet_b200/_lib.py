@@ -30,6 +30,9 @@ SIGNATURES = {
     "jdet_nms_rotated_ex": (_i, [_p, _i, _i, _p, _f, _i, _p, _p, _sz, _p]),
     "jdet_argsort_desc_workspace_bytes": (_sz, [_i]),
     "jdet_argsort_desc": (_i, [_p, _i, _p, _p, _sz, _p]),
+    "jdet_nms_poly_workspace_bytes": (_sz, [_i]),
+    "jdet_nms_poly": (_i, [_p, _i, _p, ctypes.c_double, _i, _p, _p, _sz, _p]),
+    "jdet_pack_detections": (_i, [_p, _i, _i, _p, _p, _p, _i, _p, _p]),
     "jdet_roi_align_rotated_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "jdet_roi_align_rotated": (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _i, _i, _f, _i, _p, _p, _sz, _p]),
     "jdet_roi_align_rotated_nhwc_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -587,3 +587,62 @@ JDET_API int jdet_argsort_desc(const float* scores, int n, int* order, void* wor
   JDET_RETURN_IF_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, order, n, 0, 32, st));
   return (int)cudaGetLastError();
 }
+
+// ---- detection record for the end-of-step all-gather ------------------------------------------------------
+// After NMS every rank gathers a fixed-size record per image: rows [x, y, w, h, theta, score, label] of the kept
+// detections in descending score order, zero padded to max_per_img rows, and a last row whose first column is the count
+// (what multiclass_nms_rotated's re-sort + [:max_num], ops/nms_rotated.py:584-596, leaves per image).  One CTA walks the
+// score order — already on the device from the NMS call — in blocks of 1024, compacts the kept boxes with a ballot scan
+// and writes the rows straight into the caller's (persistent) send buffer: no zeros(), argsort or index kernels in front
+// of the collective.
+namespace jdet {
+__global__ void __launch_bounds__(1024) pack_detections_kernel(const float* __restrict__ dets, int box_length,
+                                                                const float* __restrict__ scores, const int* __restrict__ order,
+                                                                const unsigned char* __restrict__ keep, int n, int max_out,
+                                                                float* __restrict__ rec) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int base = 0;
+  for (int i0 = 0; i0 < n && base < max_out; i0 += 1024) {
+    const int i = i0 + tid;
+    const int idx = i < n ? order[i] : 0;
+    const bool k = i < n && keep[idx] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_warp[lane];
+      int incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+      s_warp[lane] = incl - v;
+      if (lane == 31) s_total = incl;
+    }
+    __syncthreads();
+    const int pos = base + s_warp[warp] + __popc(bal & ((1u << lane) - 1u));
+    if (k && pos < max_out) {
+      const float* d = dets + (size_t)idx * box_length;
+      float* r = rec + (size_t)pos * 7;
+      r[0] = d[0]; r[1] = d[1]; r[2] = d[2]; r[3] = d[3]; r[4] = d[4];
+      r[5] = scores[idx];
+      r[6] = box_length == 6 ? d[5] : 0.f;
+    }
+    base += s_total;
+    __syncthreads();
+  }
+  const int count = min(base, max_out);
+  for (int r = count * 7 + tid; r < max_out * 7; r += 1024) rec[r] = 0.f;
+  if (tid < 7) rec[(size_t)max_out * 7 + tid] = tid == 0 ? (float)count : 0.f;
+}
+}  // namespace jdet
+
+// dets (n, box_length) with the label in column 5 when box_length == 6; scores (n,); order (n,) = jdet_argsort_desc(scores);
+// keep (n,) bytes from jdet_nms_rotated; record (max_per_img + 1, 7) fp32, fully written.
+JDET_API int jdet_pack_detections(const float* dets, int n, int box_length, const float* scores, const int* order,
+                                  const unsigned char* keep, int max_per_img, float* record, void* stream) {
+  if (n < 0 || max_per_img < 0 || (box_length != 5 && box_length != 6) || !record) return JDET_ERR_BAD_ARG;
+  if (n > 0 && (!dets || !scores || !order || !keep)) return JDET_ERR_BAD_ARG;
+  jdet::pack_detections_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dets, box_length, scores, order, keep, n, max_per_img, record);
+  return (int)cudaGetLastError();
+}

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
                                                             int W, int tiles_x, int tiles_y, const float* __restrict__ rois,
                                                             unsigned R, int PH, int PW, int sample_num,
                                                             unsigned char* __restrict__ tables, bool vec,
-                                                            int* __restrict__ work_counter, int pcap, int pxbytes,
+                                                            int* __restrict__ work_counter, int pcap, int pxbytes, int rec_pitch,
                                                             const __grid_constant__ RoiLevels L) {
   extern __shared__ __align__(128) unsigned char smem[];
   if ((int)blockIdx.x < tiles_x) {
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
   int4* hdr = reinterpret_cast<int4*>(smem);                       // the record, in its final layout (roi_gather_tma.cuh)
   int* cnt = reinterpret_cast<int*>(smem + RL.cnt_off);
   int2* fin = reinterpret_cast<int2*>(smem + RL.fin_off);
-  int2* raw = reinterpret_cast<int2*>(smem + RL.max_bytes);
+  int2* raw = reinterpret_cast<int2*>(smem + rec_pitch);   // rec_pitch: bytes per record in `tables` (without the pixel lists when nothing is staged)
   g4::ChunkScratch* scratch = reinterpret_cast<g4::ChunkScratch*>(raw + nbins * tpb);
   if (threadIdx.x == 0) hdr[0] = make_int4(g.batch, __float_as_int(g.inv_count), fstride, level);
   const int Hl = L.lv[level].H, Wl = L.lv[level].W;
@@ -354,8 +354,7 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
     if (threadIdx.x == 0) hdr[1] = make_int4(0, 0, 0, bytes);
     __syncthreads();
   }
-  const size_t stride = (size_t)RL.max_bytes;
-  int4* dst = reinterpret_cast<int4*>(tables + (size_t)idx * stride);
+  int4* dst = reinterpret_cast<int4*>(tables + (size_t)idx * (size_t)rec_pitch);
   for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = hdr[i];
   if (threadIdx.x == 0) work_counter[64 + (size_t)(kRoiBuckets + 1) * R + idx] = bytes;
   if (staged) {
@@ -776,7 +775,8 @@ static StagedCfg staged_cfg(int C, int PH, int PW, int sample_num) {
   const int nbins = (int)nbins_ll, tpb = 4 * sample_num * sample_num;
   c.slab = (C % 128 == 0) ? 128 : 64;
   c.pxbytes = c.slab * 4;
-  c.stride = roi_table_stride(nbins, sample_num);
+  c.stride = roi_tma_enabled() ? roi_table_stride(nbins, sample_num)      // record pitch: with / without the staged path's pixel lists
+                               : (size_t)g4::rec_layout(nbins, roi_table_fstride(sample_num), tpb).cnpx_off;
   const size_t fixed = 2 * ((((size_t)c.slab * (nbins | 1) + 3) & ~(size_t)3) * 4) + g4::kTB * c.stride + 2560;   // + the kernel's static shared memory
   for (unsigned ring = 128u << 10; ring >= (32u << 10); ring >>= 1) {
     if (fixed + ring > 227u * 1024) continue;
@@ -843,10 +843,10 @@ static cudaError_t launch_prologue(int version, const float* input_nchw, float* 
                                sizeof(float) * 32 * (kTileW + 1));
   if (version == 1) {
     if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-    roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, roi_tma_enabled() ? cfg.pcap : 0, cfg.pxbytes, L);
+    roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, roi_tma_enabled() ? cfg.pcap : 0, cfg.pxbytes, (int)cfg.stride, L);
   } else {
     if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-    roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, roi_tma_enabled() ? cfg.pcap : 0, cfg.pxbytes, L);
+    roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, roi_tma_enabled() ? cfg.pcap : 0, cfg.pxbytes, (int)cfg.stride, L);
   }
   return cudaGetLastError();
 }

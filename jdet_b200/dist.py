@@ -55,3 +55,41 @@ def unpack_detections(gathered):
         k = int(gathered[r, -1, 0].item())
         res.append(gathered[r, :k])
     return res
+
+
+# ---- the fused path: NMS epilogue -> persistent send buffer -> one collective ------------------------------------------
+_BUFFERS = {}
+
+
+def gather_buffers(device, images_per_rank, max_per_img, world):
+    """Persistent (send, recv) tensors of one rank: send (images_per_rank, max_per_img + 1, 7), recv (world, ...) — allocated
+    once per shape, so the NMS epilogue (ops.nms_rotated.ml_nms_rotated_record) writes its records where the collective
+    reads them and NCCL sees the same addresses every step."""
+    key = (str(device), images_per_rank, max_per_img, world)
+    if key not in _BUFFERS:
+        send = torch.zeros((images_per_rank, max_per_img + 1, 7), dtype=torch.float32, device=device)
+        recv = torch.zeros((world,) + tuple(send.shape), dtype=torch.float32, device=device)
+        _BUFFERS[key] = (send, recv)
+    return _BUFFERS[key]
+
+
+def all_gather_records(send, recv, group=None):
+    """ONE all_gather_into_tensor of the rank's record block; world 1 (or no process group): a view of `send`."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return send.unsqueeze(0)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+    return recv
+
+
+def nms_and_gather(per_image, iou_threshold, max_per_img=2000, group=None):
+    """per_image: list of (boxes (n,5), scores (n,), labels (n,)) of this rank's images.  Per-class rotated NMS of each
+    image written as a record straight into the send buffer, then one collective.
+    -> (world, images_per_rank, max_per_img + 1, 7)"""
+    from .ops.nms_rotated import ml_nms_rotated_record
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = per_image[0][0].device
+    send, recv = gather_buffers(dev, len(per_image), max_per_img, world)
+    for i, (b, sc, lb) in enumerate(per_image):
+        ml_nms_rotated_record(b, sc, lb, iou_threshold, max_per_img, out=send[i])
+    return all_gather_records(send, recv, group)

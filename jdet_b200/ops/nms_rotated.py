@@ -73,6 +73,36 @@ def py_cpu_nms_obb(dets, thresh):
     return torch.where(nms_rotated_cpu(boxes, order, thresh, box_length=5))[0]
 
 
+def _nms_poly(dets, thresh, fast):
+    require_cuda(dets)
+    if dets.numel() == 0:
+        return torch.zeros((0,), dtype=torch.int64, device=dets.device)
+    d = f32c(dets)
+    assert d.dim() == 2 and d.shape[1] == 9, "dets must be (n, 9): 4 corner points + score"
+    n = d.shape[0]
+    order = argsort_desc(d[:, 8].contiguous())
+    keep = torch.empty((n,), dtype=torch.bool, device=d.device)
+    L = lib()
+    with torch.cuda.device(d.device):
+        ws = scratch(L.jdet_nms_poly_workspace_bytes(n), d.device)
+        check(L.jdet_nms_poly(d.data_ptr(), n, order.data_ptr(), float(thresh), int(fast), keep.data_ptr(), ws.data_ptr(),
+                              ws.numel(), stream_ptr(d.device)), "nms_poly")
+    kept = order.long()[keep[order.long()]]            # kept indices in descending score order, like the reference's `keep` list
+    return kept
+
+
+def py_cpu_nms_poly_fast(dets, thresh):
+    """Tile -> image merge NMS over quadrilaterals (data/devkits/result_merge.py:69-131): dets (n,9) = 4 corner points + score
+    -> kept indices in descending score order (the order the reference appends them).  Bounding-box pre-filter, then
+    iou_poly (ops/nms_poly.py:247-252) on the survivors, suppress on iou > thresh — on the GPU, in binary64."""
+    return _nms_poly(dets, thresh, True)
+
+
+def py_cpu_nms_poly(dets, thresh):
+    """result_merge.py:33-66: the same without the bounding-box pre-filter."""
+    return _nms_poly(dets, thresh, False)
+
+
 def ml_nms_rotated(dets, scores, labels, iou_threshold):
     assert dets.numel() > 0 and dets.dim() == 2              # nms_rotated.py:516
     assert dets.dtype == scores.dtype                         # :517
@@ -81,6 +111,31 @@ def ml_nms_rotated(dets, scores, labels, iou_threshold):
     order_t = argsort_desc(scores)
     keep = nms_rotated_cuda(d, order_t, iou_threshold, box_length=6)
     return torch.where(keep)[0]
+
+
+def ml_nms_rotated_record(dets, scores, labels, iou_threshold, max_per_img=2000, out=None):
+    """ml_nms_rotated + the tail of multiclass_nms_rotated (re-sort by score, [:max_per_img], :584-596) as a fixed-size
+    record (max_per_img + 1, 7): rows [x,y,w,h,theta,score,label] of the kept boxes in descending score order, zero
+    padded, last row = count.  Three library calls (argsort, NMS, pack), no host sync, no index kernels; `out` may be a
+    slice of a persistent send buffer (jdet_b200.dist.all_gather_records)."""
+    require_cuda(dets, scores, labels)
+    if out is None:
+        out = torch.empty((max_per_img + 1, 7), dtype=torch.float32, device=dets.device)
+    assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (max_per_img + 1, 7)
+    n = dets.shape[0]
+    L = lib()
+    if n == 0:
+        out.zero_()
+        return out
+    assert dets.dim() == 2 and dets.dtype == scores.dtype
+    d = torch.cat([f32c(dets), labels.to(torch.float32).unsqueeze(1)], dim=1)
+    s = f32c(scores).reshape(-1)
+    order_t = argsort_desc(s)
+    keep = nms_rotated_cuda(d, order_t, iou_threshold, box_length=6)
+    with torch.cuda.device(d.device):
+        check(L.jdet_pack_detections(d.data_ptr(), n, 6, s.data_ptr(), order_t.data_ptr(), keep.data_ptr(), max_per_img,
+                                     out.data_ptr(), stream_ptr(d.device)), "pack_detections")
+    return out
 
 
 def nms_rotated(dets, scores, iou_threshold):

@@ -6,7 +6,9 @@
   forward, so it is plain torch indexing here, not a kernel.
 * ``ORConv2d`` — conv2d with the ARF-rotated weight;  ``RotationInvariantPooling`` — max over the
   orientation group (the reference's 1x1 conv there is commented out, :612-614).
-RIE (rotation-invariant encoding) is not used by S2ANet and is not mirrored.
+* ``rotation_invariant_encoding(input, nOrientation)`` / ``RotationInvariantEncoding`` — RIE (orn.py:291-330, 505-531, 582-593):
+  per (batch, feature) the orientation responses are rolled so that the strongest comes first; returns the aligned
+  features and the uint8 main directions.  Not on S2ANet's path (it uses the pooling variant); mirrored for completeness.
 """
 import math
 
@@ -77,6 +79,38 @@ class ORConv2d(nn.Conv2d):
 
     def forward(self, input):
         return F.conv2d(input, self.rotate_arf(), self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+    execute = forward
+
+
+def rotation_invariant_encoding(input, nOrientation):
+    """input (nBatch, nFeature * nOrientation, 1, 1) -> (aligned, mainDirection (nBatch, nFeature) uint8).
+    mainDirection = first index of the maximum over the orientation group (strict '>' scan from -FLT_MAX, orn.py:306-315);
+    aligned[.., (l - d) mod nOri] = input[.., l] (:316-325).  Differentiable w.r.t. input (the gather is the
+    reference's rie_backward, :332-360)."""
+    assert input.dim() == 4, "only supports a batch of RIEs."
+    assert input.size(2) == 1 and input.size(3) == 1, "mH x mW should be 1x1."
+    n_batch, n_channel = input.size(0), input.size(1)
+    n_feature = n_channel // nOrientation
+    f = input.reshape(n_batch, n_feature, nOrientation)
+    # the reference starts from maxVal = -FLT_MAX and updates on '>': -FLT_MAX / -inf / NaN entries never win; the first maximum does
+    key = torch.where(f > -torch.finfo(f.dtype).max, f, torch.full_like(f, -float("inf")))
+    d = torch.argmax(key, dim=2)                                  # first occurrence of the maximum
+    d = torch.where(torch.isneginf(key.max(dim=2)[0]), torch.zeros_like(d), d)   # no entry above -FLT_MAX: direction stays 0 (zero-initialised output)
+    src = (torch.arange(nOrientation, device=f.device)[None, None, :] + d[..., None]) % nOrientation
+    aligned = torch.gather(f, 2, src)                             # aligned[a] = f[(a + d) mod nOri]
+    return aligned.reshape(input.shape), d.to(torch.uint8)
+
+
+class RotationInvariantEncoding(nn.Module):
+    def __init__(self, nOrientation, return_direction=False):
+        super().__init__()
+        self.nOrientation = nOrientation
+        self.return_direction = return_direction
+
+    def forward(self, input):
+        output, d = rotation_invariant_encoding(input, self.nOrientation)
+        return (output, d) if self.return_direction else output
 
     execute = forward
 

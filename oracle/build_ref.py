@@ -103,7 +103,7 @@ using std::min; using std::max;
 # CPU library: reference cpu_header / cpu_src of box_iou_rotated(.py:312-326,487-500),
 # box_iou_rotated_v1 and nms_rotated (.py:314-328,414-449), BOX_LENGTH 5 and 6.
 # --------------------------------------------------------------------------------------------
-def gen_cpu(iou0, iou1, nms):
+def gen_cpu(iou0, iou1, nms, orn=None):
     parts = [PRELUDE]
 
     def iou_ns(ns, env):
@@ -140,6 +140,29 @@ static void run(const float* dets_p, int dets_shape0, const int* order_t_p,
 }}
 static float one(const float* a, const float* b) {{ return single_box_iou_rotated<float>(a, b); }}
 }}  // namespace
+""")
+    if orn is not None:
+        # ORN (ops/orn.py): ARF_forward_cpu_kernel :136-170, RIE_forward_cpu_kernel :291-330 — the reference's CPU sources
+        parts.append(f"""
+#include <cfloat>
+namespace ref_orn_cpu {{
+namespace arf {{
+{strip_jittor(orn["ARF_CPU_HEADER"])}
+}}
+namespace rie {{
+{strip_jittor(orn["RIE_CPU_HEADER"])}
+}}
+}}  // namespace ref_orn_cpu
+extern "C" {{
+// weight (nOut, nIn, nOri, kH, kW), indices (nOri, kH, kW, nRot) uint8 1-based -> out (nOut*nRot, nIn*nOri, kH, kW), pre-zeroed by the caller
+void ref_arf_forward_cpu(const float* w, const unsigned char* ind, int nOut, int nIn, int nOri, int kH, int kW, int nRot, float* out) {{
+  ref_orn_cpu::arf::ARF_forward_cpu_kernel<float>(w, ind, nOut, nIn, nOri, kH, kW, nRot, out);
+}}
+// feature (nBatch, nFeature*nOri) -> mainDirection (nBatch, nFeature) uint8, aligned (nBatch, nFeature*nOri)
+void ref_rie_forward_cpu(const float* f, unsigned char* dir, float* aligned, int nOri, int nBatch, int nFeature) {{
+  ref_orn_cpu::rie::RIE_forward_cpu_kernel<float>(f, dir, aligned, nOri, nBatch, nFeature);
+}}
+}}
 """)
     parts.append(r"""
 extern "C" {
@@ -451,11 +474,12 @@ def build(force=False, verbose=True):
     ra1 = module_strings(os.path.join(REF_OPS, "roi_align_rotated_v1.py"))
     fr = module_strings(os.path.join(REF_OPS, "fr.py"))
     dcn = module_strings(os.path.join(REF_OPS, "dcn_v1.py"))
+    orn = module_strings(os.path.join(REF_OPS, "orn.py"))
     tmp = tempfile.mkdtemp(prefix="jdet_ref_build_")
     try:
         cpu_cc = os.path.join(tmp, "ref_cpu.cc")
         with open(cpu_cc, "w") as f:
-            f.write(gen_cpu(iou0, iou1, nms))
+            f.write(gen_cpu(iou0, iou1, nms, orn))
         run(["g++"] + CPU_FLAGS + [cpu_cc, "-o", cpu_so])
         cuda_cu = os.path.join(tmp, "ref_cuda.cu")
         with open(cuda_cu, "w") as f:

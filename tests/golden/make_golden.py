@@ -102,6 +102,24 @@ def main():
                         k2_iou=k2_out, k2_keep=np.array([2]), k3_a=k3a, k3_b=k3b, k3_iou=k3)
     print("K1", k1_out.ravel(), "K2", k2_out.ravel(), "K3", k3)
 
+    # ORN: the reference's ARF / RIE CPU sources (ops/orn.py:136-170, 291-330) on small seeded inputs
+    import torch
+    from oracle import glue
+    from jdet_b200.ops.orn import arf_indices
+    rng = np.random.default_rng(5)
+    orn = {}
+    for t, (no, ni, nori, nrot, k) in enumerate(((4, 3, 1, 8, 3), (2, 3, 8, 8, 3), (3, 2, 4, 4, 3), (2, 2, 8, 8, 1))):
+        w = rng.standard_normal((no, ni, nori, k, k)).astype(np.float32)
+        ind = arf_indices(nori, nrot, (k, k)).numpy()
+        orn["arf%d_w" % t], orn["arf%d_ind" % t], orn["arf%d_out" % t] = w, ind, glue.ref_arf_forward(w, ind)
+    for t, (nb, nf, nori) in enumerate(((5, 7, 8), (3, 4, 4), (2, 16, 8))):
+        f = rng.standard_normal((nb, nf * nori)).astype(np.float32)
+        f[0, :nori] = f[0, 0]                                   # a tie: the first maximum wins
+        d, al = glue.ref_rie_forward(f, nori)
+        orn["rie%d_f" % t], orn["rie%d_nori" % t], orn["rie%d_dir" % t], orn["rie%d_out" % t] = f, np.int32(nori), d, al
+    np.savez_compressed(os.path.join(HERE, "ref_cpu_orn.npz"), **orn)
+    print("ORN golden:", sorted(orn)[:4], "...")
+
 
 if __name__ == "__main__":
     main()

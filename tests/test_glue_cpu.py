@@ -1,0 +1,85 @@
+"""CPU: the torch mirrors of the reference's glue (ORN ARF / RIE, box coders) against oracle.glue and the golden vectors
+produced by the reference's own compiled CPU sources (tests/golden/ref_cpu_orn.npz, tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import glue
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_arf_and_rie_match_compiled_reference_golden():
+    from jdet_b200.ops.orn import RotationInvariantEncoding, active_rotating_filter, rotation_invariant_encoding
+    z = np.load(os.path.join(GOLD, "ref_cpu_orn.npz"))
+    for t in range(4):
+        w, ind, want = z["arf%d_w" % t], z["arf%d_ind" % t], z["arf%d_out" % t]
+        assert np.array_equal(active_rotating_filter(torch.from_numpy(w), torch.from_numpy(ind)).numpy(), want)
+        assert np.array_equal(glue.arf_forward(w, ind), want)                      # the restatement is pinned too
+        live = glue.ref_arf_forward(w, ind)
+        assert live is None or np.array_equal(live, want)
+    for t in range(3):
+        f, nori = z["rie%d_f" % t], int(z["rie%d_nori" % t])
+        out, d = rotation_invariant_encoding(torch.from_numpy(f)[:, :, None, None], nori)
+        assert np.array_equal(d.numpy(), z["rie%d_dir" % t]) and np.array_equal(out.numpy()[:, :, 0, 0], z["rie%d_out" % t])
+        d2, a2 = glue.rie_forward(f, nori)
+        assert np.array_equal(d2, z["rie%d_dir" % t]) and np.array_equal(a2, z["rie%d_out" % t])
+        m = RotationInvariantEncoding(nori, return_direction=True)
+        o3, d3 = m(torch.from_numpy(f)[:, :, None, None])
+        assert torch.equal(o3, out) and torch.equal(d3, d)
+
+
+def test_rie_gradient_is_the_inverse_roll():
+    """rie_backward (ops/orn.py:332-360): gradInput[.., (l + d) mod nOri] = gradOutput[.., l]"""
+    from jdet_b200.ops.orn import rotation_invariant_encoding
+    g = torch.Generator().manual_seed(0)
+    f = torch.randn((4, 24, 1, 1), generator=g, requires_grad=True)
+    out, d = rotation_invariant_encoding(f, 8)
+    go = torch.randn(out.shape, generator=g)
+    out.backward(go)
+    want = torch.zeros(4, 3, 8)
+    gov, dv = go.reshape(4, 3, 8), d.long()
+    for i in range(4):
+        for j in range(3):
+            for l in range(8):
+                want[i, j, (l + int(dv[i, j])) % 8] = gov[i, j, l]
+    assert torch.equal(f.grad.reshape(4, 3, 8), want)
+
+
+def test_box_coders_match_glue_restatement():
+    from jdet_b200.models.boxes import AnchorGeneratorRotatedS2ANet, delta2bbox_rotated
+    from jdet_b200.models.roi_heads import bbox_decode
+    rng = np.random.default_rng(1)
+    rois = np.concatenate([rng.uniform(0, 500, (200, 2)), rng.uniform(4, 200, (200, 2)), rng.uniform(-1.6, 1.6, (200, 1))], 1).astype(np.float32)
+    deltas = (rng.standard_normal((200, 5)) * 0.5).astype(np.float32)
+    got = delta2bbox_rotated(torch.from_numpy(rois), torch.from_numpy(deltas), stds=(.1, .1, .2, .2, .1)).numpy()
+    want = glue.delta2bbox_rotated(rois, deltas, stds=(.1, .1, .2, .2, .1))
+    ang = np.abs(np.mod(got[:, 4] - want[:, 4] + np.pi / 2, np.pi) - np.pi / 2)
+    assert np.allclose(got[:, :4], want[:, :4], rtol=2e-5, atol=2e-4) and ang.max() < 1e-4
+    gen = AnchorGeneratorRotatedS2ANet(4, [4.0], [1.0], angles=[0.0])
+    anchors = gen.grid_anchors((6, 7), 8)
+    preds = (rng.standard_normal((2, 5, 6, 7)) * 0.3).astype(np.float32)
+    assert np.allclose(bbox_decode(torch.from_numpy(preds), anchors).numpy(), glue.bbox_decode(preds, anchors.numpy()), rtol=2e-5, atol=2e-4)
+
+
+def test_iou_poly_restatement_known_answers():
+    """oracle.glue.iou_poly (the restated shapely arithmetic, ops/nms_poly.py:247-252): analytic cases, orientation
+    independence, and agreement with the pinned box_iou_rotated oracle on rectangles."""
+    import oracle
+    from jdet_b200.models.boxes import rotated_box_to_poly
+    sq = np.array([0, 0, 2, 0, 2, 2, 0, 2], np.float64)
+    assert glue.iou_poly(sq, sq) == 1.0
+    assert glue.iou_poly(sq, sq + np.tile([1.0, 0.0], 4)) == 2.0 / 6.0              # half overlap: 2 / (4 + 4 - 2)
+    assert glue.iou_poly(sq, sq + np.tile([2.0, 0.0], 4)) == 0.0                    # touching edges
+    assert glue.iou_poly(sq, sq[[6, 7, 4, 5, 2, 3, 0, 1]] + np.tile([1.0, 0.0], 4)) == 2.0 / 6.0   # clockwise input
+    tri_like = np.array([0, 0, 4, 0, 4, 4, 0, 0.001], np.float64)                   # general convex quadrilateral
+    assert abs(glue.iou_poly(sq, tri_like) - glue.iou_poly(tri_like, sq)) < 1e-15
+    tiny = sq * 1e-3                                                                 # union < 0.01: the max(., 0.01) clamp
+    assert glue.iou_poly(tiny, tiny) == (4e-6) / 0.01
+    rng = np.random.default_rng(4)
+    b = np.concatenate([rng.uniform(0, 60, (40, 2)), rng.uniform(4, 40, (40, 2)), rng.uniform(-1.5, 1.5, (40, 1))], 1).astype(np.float32)
+    polys = rotated_box_to_poly(torch.from_numpy(b)).numpy()
+    want = oracle.box_iou_rotated(b, b, 0, oracle.VARIANT_CUDA)
+    got = np.array([[glue.iou_poly(polys[i], polys[j]) for j in range(40)] for i in range(40)])
+    assert np.abs(got - want).max() < 2e-5                                           # float32 corners vs the fp32 rectangle routine

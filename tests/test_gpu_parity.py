@@ -706,16 +706,32 @@ def test_ops_are_cuda_graph_capturable():
     rois = cu(_rois(rng, 300, 1, 192.0, 8, 96))
     b1, b2 = cu(dota_boxes(rng, 200, 300.0)), cu(dota_boxes(rng, 150, 300.0))
     boxes = cu(s2anet_anchors(rng, 1, 48, 48, 8)[..., [1, 0, 2, 3, 4]].copy())
-    eager = (ops().roi_align_rotated_v1.roi_align(x, rois, (7, 7), 0.25, 2), ops().box_iou_rotated(b1, b2),
-             ops().fr.feature_refine(x, boxes, 1 / 8., 1))
+    from jdet_b200.models.roi_heads.s2anet_head import AlignConv
+    n = 4000
+    d6 = cu(np.concatenate([clustered_boxes(rng, n // 2, 20, 400.0), dota_boxes(rng, n - n // 2, 400.0),
+                            ], 0))
+    d6 = torch.cat([d6, cu(rng.integers(0, 15, n).astype(np.float32))[:, None]], 1).contiguous()
+    sc = cu(tie_free_scores(rng, n))
+    lab = d6[:, 5].to(torch.int64)
+    anchors = cu(s2anet_anchors(rng, 1, 48, 48, 8))
+    ac = AlignConv(128, 64, 3).cuda().requires_grad_(False)
+
+    def run_all():
+        order = ops().nms_rotated.argsort_desc(sc)
+        return (ops().roi_align_rotated_v1.roi_align(x, rois, (7, 7), 0.25, 2), ops().box_iou_rotated(b1, b2),
+                ops().fr.feature_refine(x, boxes, 1 / 8., 1), ops().fr.feature_refine(x, boxes, 1 / 8., 5),
+                ops().nms_rotated.nms_rotated_cuda(d6, order, 0.1, 6).to(torch.float32),       # argsort + NMS: keep mask, no host sync
+                ops().nms_rotated.ml_nms_rotated_record(d6[:, :5].contiguous(), sc, lab, 0.1, 500),   # + the pack into a send record
+                ac(x, anchors, 8))                                                              # fused tcgen05 AlignConv
+
+    eager = run_all()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
         with torch.cuda.graph(g, stream=s):
-            cap = (ops().roi_align_rotated_v1.roi_align(x, rois, (7, 7), 0.25, 2), ops().box_iou_rotated(b1, b2),
-                   ops().fr.feature_refine(x, boxes, 1 / 8., 1))
+            cap = run_all()
     for t in cap:
         t.zero_()
     g.replay()
@@ -788,3 +804,195 @@ def test_nms_cpu_path_golden():
         for bl, d in ((5, d6[:, :5]), (6, d6)):
             keep = ops().nms_rotated.nms_rotated_cpu(cu(d), order, thr, box_length=bl).cpu().numpy()
             assert np.array_equal(keep, g["keep%d_cpu_thr%02d" % (bl, int(thr * 10))])
+
+
+# ------------------------------------------------------------------------------------ NMS -> record -> all-gather
+@pytest.mark.parametrize("n,max_per_img", [(5000, 2000), (3000, 100), (40, 2000), (1, 5)])
+def test_nms_record_matches_eager_pack(n, max_per_img):
+    """ml_nms_rotated_record (argsort + NMS + one pack launch into the send buffer) == ml_nms_rotated followed by the eager
+    torch packing, bit for bit; and == the oracle's multiclass tail (re-sort by score, truncate)."""
+    from jdet_b200 import dist as jdist
+    rng = np.random.default_rng(n)
+    d = np.concatenate([clustered_boxes(rng, n // 2 + 1, 25, 600.0), dota_boxes(rng, n, 600.0)])[:n]
+    s, l = tie_free_scores(rng, n), rng.integers(0, 15, n)
+    td, ts, tl = cu(d), cu(s), cu(l, torch.int64)
+    buf = torch.full((3, max_per_img + 1, 7), 7.0, device="cuda")              # a dirty persistent buffer: every byte is rewritten
+    rec = ops().nms_rotated.ml_nms_rotated_record(td, ts, tl, 0.1, max_per_img, out=buf[1])
+    keep = ops().nms_rotated.ml_nms_rotated(td, ts, tl, 0.1)
+    want = jdist.pack_detections(td, ts, tl, keep, max_per_img)
+    assert rec.data_ptr() == buf[1].data_ptr()
+    assert np.array_equal(bits(rec.cpu().numpy()), bits(want.cpu().numpy()))
+    assert float(buf[0].min()) == 7.0 and float(buf[2].min()) == 7.0          # neighbours untouched
+    ko = oracle.ml_nms_rotated(d, s, l, 0.1)
+    order = ko[np.argsort(-s[ko], kind="stable")][:max_per_img]
+    got = rec.cpu().numpy()
+    assert int(got[-1, 0]) == len(order)
+    assert np.array_equal(got[:len(order), :5], d[order]) and np.array_equal(got[:len(order), 6], l[order].astype(np.float32))
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    import torch.distributed as dist
+    from jdet_b200 import dist as jdist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        outs = []
+        for step in range(2):
+            imgs = []
+            for i in range(2):
+                d, s, l = _image_dets(100 * step + 2 * rank + i)
+                imgs.append((cu(d).cuda(rank), cu(s).cuda(rank), cu(l, torch.int64).cuda(rank)))
+            outs.append(jdist.nms_and_gather(imgs, 0.1, 300).cpu().numpy().copy())
+        q.put((rank, outs))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _image_dets(seed):
+    rng = np.random.default_rng(seed)
+    n = 1500 + 37 * (seed % 5)
+    d = np.concatenate([clustered_boxes(rng, n // 2, 25, 800.0), dota_boxes(rng, n - n // 2, 800.0)])
+    return d, tie_free_scores(rng, n), rng.integers(0, 15, n)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL)")
+def test_nccl_gathered_detections_equal_single_gpu():
+    """SURVEY 8e parity criterion: the detections gathered over NCCL equal the single-GPU run image by image."""
+    import socket
+    import torch.multiprocessing as mp
+    from jdet_b200 import dist as jdist
+    sck = socket.socket(); sck.bind(("127.0.0.1", 0)); port = sck.getsockname()[1]; sck.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for step in range(2):
+        assert np.array_equal(got[0][step], got[1][step])
+        for r in range(2):
+            for i in range(2):
+                d, s, l = _image_dets(100 * step + 2 * r + i)
+                want = ops().nms_rotated.ml_nms_rotated_record(cu(d), cu(s), cu(l, torch.int64), 0.1, 300).cpu().numpy()
+                assert np.array_equal(bits(got[0][step][r, i]), bits(want))
+                ko = oracle.ml_nms_rotated(d, s, l, 0.1)
+                assert int(want[-1, 0]) == min(len(ko), 300)
+
+
+# ------------------------------------------------------------------------------------ parity of the torch glue on the GPU
+def test_feature_refine_module_numeric():
+    """FeatureRefineModule (ops/fr.py:291-347) against oracle.glue: float64 numpy convolutions + the oracle's feature_refine."""
+    from oracle import glue
+    rng = np.random.default_rng(9)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        m = ops().fr.FeatureRefineModule(16, [8, 16]).cuda()
+        with torch.no_grad():
+            for p_ in m.parameters():
+                p_.copy_(torch.randn_like(p_) * 0.2)
+        xs = [rng.standard_normal((2, 16, 16, 16)).astype(np.float32), rng.standard_normal((2, 16, 8, 8)).astype(np.float32)]
+        boxes = [[s2anet_anchors(rng, 1, 16, 16, 8).reshape(-1, 5)[:, [1, 0, 2, 3, 4]].copy(),
+                  s2anet_anchors(rng, 1, 8, 8, 16).reshape(-1, 5)[:, [1, 0, 2, 3, 4]].copy()] for _ in range(2)]
+        with torch.no_grad():
+            out = m([cu(x) for x in xs], [[cu(b) for b in img] for img in boxes])
+        g = lambda t: t.detach().cpu().double().numpy()
+        want = glue.feature_refine_module(xs, boxes, [8, 16], g(m.conv_5_1.weight), g(m.conv_5_1.bias), g(m.conv_1_5.weight),
+                                          g(m.conv_1_5.bias), g(m.conv_1_1.weight), g(m.conv_1_1.bias), oracle.feature_refine)
+        for o, w in zip(out, want):
+            assert tuple(o.shape) == w.shape
+            assert np.abs(o.cpu().numpy() - w).max() <= TOL, np.abs(o.cpu().numpy() - w).max()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_bbox_decode_and_delta2bbox_on_gpu():
+    """bbox_decode / delta2bbox_rotated (s2anet_head.py:631-654, box_ops.py:229-285) run on the GPU against oracle.glue."""
+    from oracle import glue
+    from jdet_b200.models.boxes import AnchorGeneratorRotatedS2ANet, delta2bbox_rotated
+    from jdet_b200.models.roi_heads import bbox_decode
+    rng = np.random.default_rng(3)
+    gen = AnchorGeneratorRotatedS2ANet(4, [4.0], [1.0], angles=[0.0])
+    anchors = gen.grid_anchors((20, 24), 8)
+    preds = (rng.standard_normal((3, 5, 20, 24)) * 0.4).astype(np.float32)
+    preds[0, 2:4, :3, :3] = 30.0                                            # clipped by wh_ratio_clip = 1e-6 (|dw| <= 13.8)
+    got = bbox_decode(cu(preds), anchors.cuda()).cpu().numpy()
+    want = glue.bbox_decode(preds, anchors.numpy())
+    assert got.shape == want.shape == (3, 20, 24, 5)
+    assert np.allclose(got, want, rtol=2e-5, atol=2e-4)
+    rois = np.concatenate([rng.uniform(0, 800, (500, 2)), rng.uniform(4, 300, (500, 2)), rng.uniform(-1.6, 1.6, (500, 1))], 1).astype(np.float32)
+    deltas = (rng.standard_normal((500, 5)) * 0.5).astype(np.float32)
+    stds = (0.1, 0.1, 0.2, 0.2, 0.1)
+    got = delta2bbox_rotated(cu(rois), cu(deltas), stds=stds, wh_ratio_clip=16 / 1000).cpu().numpy()
+    want = glue.delta2bbox_rotated(rois, deltas, stds=stds, wh_ratio_clip=16 / 1000)
+    ang = np.abs(np.mod(got[:, 4] - want[:, 4] + np.pi / 2, np.pi) - np.pi / 2)   # the angle wraps at the range ends
+    assert np.allclose(got[:, :4], want[:, :4], rtol=2e-5, atol=2e-4) and ang.max() < 1e-4
+
+
+def test_orn_on_gpu_against_compiled_reference():
+    """ORConv2d's ARF rotation and RIE on the GPU == the reference's compiled CPU sources (golden: tests/golden/ref_cpu_orn.npz)."""
+    from jdet_b200.ops.orn import active_rotating_filter, rotation_invariant_encoding
+    z = np.load(os.path.join(GOLD, "ref_cpu_orn.npz"))
+    for t in range(4):
+        got = active_rotating_filter(cu(z["arf%d_w" % t]), torch.as_tensor(z["arf%d_ind" % t]).cuda()).cpu().numpy()
+        assert np.array_equal(bits(got), bits(z["arf%d_out" % t]))
+    for t in range(3):
+        f, nori = z["rie%d_f" % t], int(z["rie%d_nori" % t])
+        out, d = rotation_invariant_encoding(cu(f)[:, :, None, None], nori)
+        assert np.array_equal(d.cpu().numpy(), z["rie%d_dir" % t])
+        assert np.array_equal(bits(out.cpu().numpy()[:, :, 0, 0]), bits(z["rie%d_out" % t]))
+
+
+def test_nms_scan_handoff_stress():
+    """nms_scan_kernel publishes kept(cb) between warps through shared memory (volatile + __threadfence_block; racecheck
+    flags it, profiles/r01_sanitizer_reentry.txt).  1000 repetitions over many classes x many column blocks, dense clusters:
+    every keep mask must hash identically (and equal the oracle's)."""
+    rng = np.random.default_rng(123)
+    n = 24000
+    d = np.concatenate([clustered_boxes(rng, n * 3 // 4, 60, 900.0), dota_boxes(rng, n - n * 3 // 4, 900.0)])
+    s, l = tie_free_scores(rng, n), rng.integers(0, 5, n)                  # 5 classes: ~75 column blocks per class
+    d6 = cu(np.concatenate([d, l[:, None].astype(np.float32)], 1))
+    order = ops().nms_rotated.argsort_desc(cu(s))
+    wts = torch.arange(1, n + 1, device="cuda", dtype=torch.float64)
+    first = None
+    for it in range(1000):
+        keep = ops().nms_rotated.nms_rotated_cuda(d6, order, 0.1, 6)
+        h = (keep.to(torch.float64) * wts).sum()
+        if first is None:
+            first = h.clone()
+            want = np.zeros(n, bool)
+            want[oracle.ml_nms_rotated(d, s, l, 0.1)] = True
+            assert np.array_equal(keep.cpu().numpy(), want)
+        else:
+            assert bool(h == first), it
+
+
+@pytest.mark.parametrize("fast", [True, False])
+@pytest.mark.parametrize("thr", [0.1, 0.3])
+def test_nms_poly_merge_vs_oracle(fast, thr):
+    """py_cpu_nms_poly_fast / py_cpu_nms_poly (data/devkits/result_merge.py:69-131, :33-66) on the GPU == the oracle's
+    restatement: same kept indices in the same (descending score) order.  Rectangles, jittered convex quadrilaterals,
+    clockwise inputs and duplicates."""
+    from oracle import glue
+    from jdet_b200.models.boxes import rotated_box_to_poly
+    rng = np.random.default_rng(17 + int(fast))
+    n = 700
+    b = np.concatenate([clustered_boxes(rng, n // 2, 12, 500.0), dota_boxes(rng, n - n // 2, 500.0)]).astype(np.float32)
+    polys = rotated_box_to_poly(torch.from_numpy(b)).numpy()
+    polys[::3] += rng.uniform(-0.15, 0.15, polys[::3].shape).astype(np.float32) * b[::3, 2:3].clip(max=20)   # convex, not rectangles
+    polys[1::7] = polys[1::7][:, [6, 7, 4, 5, 2, 3, 0, 1]]                           # clockwise
+    polys[5] = polys[4]                                                               # exact duplicate
+    dets = np.concatenate([polys, tie_free_scores(rng, n)[:, None]], 1).astype(np.float32)
+    fn = ops().nms_rotated.py_cpu_nms_poly_fast if fast else ops().nms_rotated.py_cpu_nms_poly
+    got = fn(cu(dets), thr).cpu().numpy()
+    want = glue.py_cpu_nms_poly_fast(dets, thr, fast=fast)
+    assert np.array_equal(got, want), (len(got), len(want))
+    assert fn(cu(dets[:0]), thr).numel() == 0
+    one = fn(cu(dets[:1]), thr).cpu().numpy()
+    assert np.array_equal(one, [0])

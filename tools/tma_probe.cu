@@ -129,6 +129,10 @@ int main(int argc, char** argv) {
 
   struct Cfg { int mode, cs, bx, by, px, stages, ctas; int g4box; int warps; };
   std::vector<Cfg> cfgs;
+  if (argc > 2 && atoi(argv[2]) == 3) {   // NCHW box sweep: which (BX, BY, CS) boxes does the tensor-map path take?
+    for (int cs : {1, 2, 4, 8, 16, 32})
+      for (int bx : {32, 64}) cfgs.push_back({3, cs, bx, 8, bx * 8 * 2, 2, 1, 0, 4});
+  } else {
   for (int warps : {1, 2, 4, 8, 16}) {
     const int ctas = 1;
     cfgs.push_back({0, 128, 0, 0, 16, 2, ctas, 0, warps});    // bulk 512 B per op
@@ -138,9 +142,7 @@ int main(int argc, char** argv) {
     cfgs.push_back({2, 64, 4, 4, 16, 2, ctas, 0, warps});     // tile 4x4x64ch 4 KB per op
     cfgs.push_back({2, 64, 2, 2, 16, 2, ctas, 0, warps});     // tile 2x2x64ch 1 KB per op
   }
-  cfgs.push_back({3, 32, 16, 8, 128, 2, 1, 0, 1});            // NCHW box 16x8x32ch (16 KB)
-  cfgs.push_back({3, 64, 4, 4, 16, 2, 1, 0, 1});              // NCHW box 4x4x64ch
-  cfgs.push_back({3, 16, 32, 4, 128, 2, 1, 0, 1});            // NCHW box 32x4x16ch: 128-B inner rows
+  }
   const int only = argc > 1 ? atoi(argv[1]) : -1;
   if (only >= (int)cfgs.size()) return 3;
   for (int ci = 0; ci < (int)cfgs.size(); ci++) {
