@@ -81,6 +81,10 @@ int jdet_nms_poly(const float* dets, int n, const int* order, double iou_thresho
  * jdet_argsort_desc(scores); keep (n,) bytes from jdet_nms_rotated; record (max_per_img + 1, 7) fp32, fully written.       */
 int jdet_pack_detections(const float* dets, int n, int box_length, const float* scores, const int* order,
                          const unsigned char* keep, int max_per_img, float* record, void* stream);
+/* one image of a batch whose boxes went through ONE jdet_nms_rotated call with labels offset per image (label' = image *
+ * num_classes + label, dets (n,6)): only boxes with label_lo <= label' < label_hi, written with label' - label_lo.       */
+int jdet_pack_detections_range(const float* dets, int n, const float* scores, const int* order, const unsigned char* keep,
+                               float label_lo, float label_hi, int max_per_img, float* record, void* stream);
 
 /* ---- roi_align_rotated -----------------------------------------------------------------------
  * replaces: version 1: _RotatedROIAlign_v1.execute ops/roi_align_rotated_v1.py:300-326 (kernel :70-147)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "jdet_argsort_desc": (_i, [_p, _i, _p, _p, _sz, _p]),
     "jdet_nms_poly_workspace_bytes": (_sz, [_i]),
     "jdet_nms_poly": (_i, [_p, _i, _p, ctypes.c_double, _i, _p, _p, _sz, _p]),
+    "jdet_pack_detections_range": (_i, [_p, _i, _p, _p, _p, _f, _f, _i, _p, _p]),
     "jdet_pack_detections": (_i, [_p, _i, _i, _p, _p, _p, _i, _p, _p]),
     "jdet_roi_align_rotated_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "jdet_roi_align_rotated": (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _i, _i, _f, _i, _p, _p, _sz, _p]),

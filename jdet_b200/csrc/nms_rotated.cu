@@ -599,7 +599,9 @@ namespace jdet {
 __global__ void __launch_bounds__(1024) pack_detections_kernel(const float* __restrict__ dets, int box_length,
                                                                 const float* __restrict__ scores, const int* __restrict__ order,
                                                                 const unsigned char* __restrict__ keep, int n, int max_out,
-                                                                float* __restrict__ rec) {
+                                                                float label_lo, float label_hi, float* __restrict__ rec) {
+  // label_hi > label_lo: only boxes whose label (column 5) lies in [label_lo, label_hi) — one image of a batch whose labels
+  // were offset per image for a single NMS call — and the record carries label - label_lo
   __shared__ int s_warp[32];
   __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -607,7 +609,8 @@ __global__ void __launch_bounds__(1024) pack_detections_kernel(const float* __re
   for (int i0 = 0; i0 < n && base < max_out; i0 += 1024) {
     const int i = i0 + tid;
     const int idx = i < n ? order[i] : 0;
-    const bool k = i < n && keep[idx] != 0;
+    bool k = i < n && keep[idx] != 0;
+    if (k && label_hi > label_lo) { const float l = dets[(size_t)idx * box_length + 5]; k = l >= label_lo && l < label_hi; }
     const unsigned bal = __ballot_sync(0xffffffffu, k);
     if (lane == 0) s_warp[warp] = __popc(bal);
     __syncthreads();
@@ -626,7 +629,7 @@ __global__ void __launch_bounds__(1024) pack_detections_kernel(const float* __re
       float* r = rec + (size_t)pos * 7;
       r[0] = d[0]; r[1] = d[1]; r[2] = d[2]; r[3] = d[3]; r[4] = d[4];
       r[5] = scores[idx];
-      r[6] = box_length == 6 ? d[5] : 0.f;
+      r[6] = box_length == 6 ? d[5] - (label_hi > label_lo ? label_lo : 0.f) : 0.f;
     }
     base += s_total;
     __syncthreads();
@@ -643,6 +646,16 @@ JDET_API int jdet_pack_detections(const float* dets, int n, int box_length, cons
                                   const unsigned char* keep, int max_per_img, float* record, void* stream) {
   if (n < 0 || max_per_img < 0 || (box_length != 5 && box_length != 6) || !record) return JDET_ERR_BAD_ARG;
   if (n > 0 && (!dets || !scores || !order || !keep)) return JDET_ERR_BAD_ARG;
-  jdet::pack_detections_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dets, box_length, scores, order, keep, n, max_per_img, record);
+  jdet::pack_detections_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dets, box_length, scores, order, keep, n, max_per_img, 0.f, 0.f, record);
+  return (int)cudaGetLastError();
+}
+
+// the same for ONE image of a batch that went through a single NMS call with per-image label offsets: only boxes with
+// label_lo <= label < label_hi (box_length 6), written with label - label_lo
+JDET_API int jdet_pack_detections_range(const float* dets, int n, const float* scores, const int* order, const unsigned char* keep,
+                                        float label_lo, float label_hi, int max_per_img, float* record, void* stream) {
+  if (n < 0 || max_per_img < 0 || !record || !(label_hi > label_lo)) return JDET_ERR_BAD_ARG;
+  if (n > 0 && (!dets || !scores || !order || !keep)) return JDET_ERR_BAD_ARG;
+  jdet::pack_detections_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(dets, 6, scores, order, keep, n, max_per_img, label_lo, label_hi, record);
   return (int)cudaGetLastError();
 }

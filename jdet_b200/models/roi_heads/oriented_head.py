@@ -56,6 +56,50 @@ class OrientedHead(nn.Module):
         return torch.cat([obb2poly(boxes[valid]), fg[valid][:, None]], 1), valid.nonzero()[:, 1]
 
     @torch.no_grad()
+    def detect_records(self, feats, props, counts, iou_thr=0.1, max_per_img=2000, out=None):
+        """The inference tail in one pass over the batch: padded proposals (N, P, >=5) + counts (N,) -> fused 4-level rotated
+        RoIAlign -> shared FCs -> decode -> score threshold -> ONE per-class rotated NMS call for all images (labels offset
+        per image) -> per image a detection record [x,y,w,h,theta,score,label] x max_per_img + count row, written into
+        `out` (N, max_per_img + 1, 7) — e.g. the persistent all-gather send buffer.  One host sync (the nonzero of the
+        score threshold)."""
+        N, P = props.shape[:2]
+        dev = props.device
+        img = torch.arange(N, device=dev, dtype=props.dtype)[:, None, None].expand(N, P, 1)
+        rois = torch.cat([img, props[..., :5]], 2).reshape(N * P, 6)
+        cls_score, bbox_pred = self.forward_single(feats, rois)
+        return self.records_from_scores(rois, cls_score, bbox_pred, counts, N, P, iou_thr, max_per_img, out)
+
+    @torch.no_grad()
+    def records_from_scores(self, rois, cls_score, bbox_pred, counts, N, P, iou_thr=0.1, max_per_img=2000, out=None):
+        """decode -> score threshold -> one rotated NMS call -> per-image records (the tail of detect_records)"""
+        from ...ops._common import check, lib, stream_ptr
+        from ...ops.nms_rotated import argsort_desc, nms_rotated_cuda
+        dev = rois.device
+        if out is None:
+            out = torch.empty((N, max_per_img + 1, 7), dtype=torch.float32, device=dev)
+        scores = cls_score.softmax(1)[:, :-1]
+        boxes = oriented_delta_xywht_decode(rois[:, 1:], bbox_pred, self.means, self.stds).reshape(N * P, -1, 5)
+        live = (torch.arange(P, device=dev)[None] < counts[:, None]).reshape(N * P, 1)
+        valid = (scores > self.score_thresh) & live
+        ri, ci = valid.nonzero(as_tuple=True)                                   # row-major (box, class), like the reference's mask
+        if ri.numel() == 0:
+            out.zero_()
+            return out
+        b = boxes[ri, ci if boxes.shape[1] > 1 else torch.zeros_like(ci)]
+        sc = scores[ri, ci].contiguous()
+        lab = (ri // P) * self.num_classes + ci                                  # image-major label: classes of different images never meet
+        d6 = torch.cat([b, lab.to(torch.float32)[:, None]], 1).contiguous()
+        order = argsort_desc(sc)
+        keep = nms_rotated_cuda(d6, order, iou_thr, box_length=6)
+        L = lib()
+        with torch.cuda.device(dev):
+            for i in range(N):
+                check(L.jdet_pack_detections_range(d6.data_ptr(), d6.shape[0], sc.data_ptr(), order.data_ptr(), keep.data_ptr(),
+                                                   float(i * self.num_classes), float((i + 1) * self.num_classes), max_per_img,
+                                                   out[i].data_ptr(), stream_ptr(dev)), "pack_detections_range")
+        return out
+
+    @torch.no_grad()
     def forward(self, feats, proposal_list, scale_factors=None):
         """feats: FPN maps (N,C,H_l,W_l); proposal_list: per image (k,>=5).  One batched pass over all images' RoIs
         (the reference loops over images, :519-535); returns per image (polys (k,8), scores (k,), labels (k,))."""

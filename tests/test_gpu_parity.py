@@ -996,3 +996,75 @@ def test_nms_poly_merge_vs_oracle(fast, thr):
     assert fn(cu(dets[:0]), thr).numel() == 0
     one = fn(cu(dets[:1]), thr).cpu().numpy()
     assert np.array_equal(one, [0])
+
+
+def test_oriented_rcnn_batched_heads_equal_per_image_path():
+    """cfg5 tail: the batched RPN (one decode, one horizontal NMS call over (image, level) groups) and the batched RoI head
+    (one rotated NMS call for all images with image-major labels, per-image range pack) give, image by image, what the
+    per-image paths give."""
+    from jdet_b200.models.roi_heads import OrientedHead, OrientedRPNHead
+    from jdet_b200.models.boxes import rectpoly2obb
+    torch.manual_seed(3)
+    rpn = OrientedRPNHead(64, nms_pre=600, nms_post=400).cuda().eval()
+    torch.nn.init.normal_(rpn.rpn_cls.weight, 0, 0.05); torch.nn.init.normal_(rpn.rpn_reg.weight, 0, 0.02)
+    head = OrientedHead(num_classes=15, in_channels=64, fc_out_channels=128).cuda().eval()
+    torch.nn.init.normal_(head.fc_cls.weight, 0, 0.05)
+    feats = [torch.randn(3, 64, 512 // s, 512 // s, device="cuda") for s in (4, 8, 16, 32, 64)]
+    single = rpn(feats)
+    props, counts = rpn.forward_batched(feats)
+    for i in range(3):
+        k = int(counts[i])
+        assert k == single[i].shape[0] and torch.equal(props[i, :k], single[i]) and float(props[i, k:].abs().max() if k < 400 else 0) == 0
+    rec = head.detect_records(feats, props, counts, 0.1, 300)
+    # the tail on the SAME class scores / regressions, image by image (the FC GEMMs are library calls whose last bits move
+    # with the batch size, so they are computed once): identical records
+    N, P = props.shape[:2]
+    rois = torch.cat([torch.arange(N, device="cuda", dtype=torch.float32)[:, None, None].expand(N, P, 1), props[..., :5]], 2).reshape(N * P, 6)
+    cls_score, bbox_pred = head.forward_single(feats, rois)
+    again = head.records_from_scores(rois, cls_score, bbox_pred, counts, N, P, 0.1, 300)
+    for i in range(3):
+        r_i = rois[i * P:(i + 1) * P].clone(); r_i[:, 0] = 0
+        one = head.records_from_scores(r_i, cls_score[i * P:(i + 1) * P], bbox_pred[i * P:(i + 1) * P], counts[i:i + 1], 1, P, 0.1, 300)
+        assert np.array_equal(bits(again[i].cpu().numpy()), bits(one[0].cpu().numpy()))
+        assert int(rec[i, -1, 0]) == int(again[i, -1, 0])
+    # and against the reference-shaped path: per-image get_bboxes -> per-class rotated NMS on the decoded boxes
+    dets = head(feats, [props[i, :int(counts[i])] for i in range(3)])
+    for i, (polys, sc, lab) in enumerate(dets):
+        k = int(rec[i, -1, 0])
+        if polys.shape[0] == 0:
+            assert k == 0
+            continue
+        keep = ops().nms_rotated.ml_nms_rotated(rectpoly2obb(polys), sc, lab, 0.1)
+        assert k == min(int(keep.numel()), 300)
+        top = torch.sort(sc[keep], descending=True, stable=True)[0][:k]
+        assert torch.allclose(rec[i, :k, 5], top, atol=0, rtol=0)
+
+
+def test_oriented_rcnn_network_runs_end_to_end():
+    """tiles in -> records out on the R50-FPN stand-in (random weights): shapes, counts within bounds, scores sorted."""
+    from jdet_b200.models.networks import OrientedRCNN
+    torch.manual_seed(0)
+    net = OrientedRCNN(max_per_img=500).cuda().eval()
+    torch.nn.init.normal_(net.rpn.rpn_cls.weight, 0, 0.05); torch.nn.init.normal_(net.roi_head.fc_cls.weight, 0, 0.05)
+    img = torch.randint(0, 256, (2, 3, 512, 512), dtype=torch.uint8, device="cuda")
+    rec = net(img)
+    assert tuple(rec.shape) == (2, 501, 7)
+    for i in range(2):
+        k = int(rec[i, -1, 0])
+        assert 0 <= k <= 500 and bool((rec[i, :k - 1, 5] >= rec[i, 1:k, 5]).all()) and float(rec[i, k:500].abs().max() if k < 500 else 0) == 0
+
+
+def test_horizontal_nms_matches_torchvision():
+    """The RPN's horizontal proposal NMS runs on the rotated-NMS kernels with theta = 0; same survivors as torchvision.ops.nms
+    with the groups kept apart by a coordinate offset (random boxes: no pair within 1e-6 of the threshold)."""
+    from torchvision.ops import nms
+    from jdet_b200.models.roi_heads.oriented_rpn_head import horizontal_nms
+    rng = np.random.default_rng(8)
+    n = 6000
+    xy = rng.uniform(0, 600, (n, 2)); wh = rng.uniform(8, 120, (n, 2))
+    hbb = cu(np.concatenate([xy, xy + wh], 1))
+    sc = cu(tie_free_scores(rng, n))
+    grp = cu(rng.integers(0, 6, n), torch.int64)
+    got = horizontal_nms(hbb, sc, grp, 0.7)
+    want = nms(hbb + (grp.float() * 2000)[:, None], sc, 0.7)
+    assert torch.equal(got, want)
