@@ -114,7 +114,16 @@ def lib():
                     raise RuntimeError(
                         "libjdet_b200.so is not built and could not be built (%s); "
                         "jdet_b200 has no CPU fallback — run `python -c 'import __graft_entry__ as g; g.build()'`" % e)
+                # a library older than the sources may not match SIGNATURES any more: tolerated only on request
+                if os.environ.get("JDET_B200_ALLOW_STALE_LIB") != "1":
+                    raise RuntimeError(
+                        "libjdet_b200.so is older than jdet_b200/csrc and the rebuild failed (%s); refusing to load a library "
+                        "whose ABI may differ from the Python bindings (set JDET_B200_ALLOW_STALE_LIB=1 to override)" % e)
+                sys.stderr.write("jdet_b200: WARNING: loading a STALE libjdet_b200.so (rebuild failed: %s)\n" % e)
         L = ctypes.CDLL(SO)
+        missing = [name for name in SIGNATURES if not hasattr(L, name)]
+        if missing:
+            raise RuntimeError("libjdet_b200.so does not export %s: it was built from other sources than these bindings" % missing)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

@@ -381,7 +381,8 @@ int align_conv_tc_launch(const float* x, const float* anchors, const float* weig
   const size_t smem = 1024 + (size_t)kStages * (2 * kABytes + 2 * (size_t)Co * kRowBytes) + 256;
   cudaError_t e = cudaFuncSetAttribute(align_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const int sms = num_sms();
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   align_conv_tc_kernel<<<grid, kThreads, smem, st>>>(p);
   return (int)cudaGetLastError();
 }

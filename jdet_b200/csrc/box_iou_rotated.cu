@@ -108,10 +108,16 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const float4 rq = s_rq[warp * 8 + k];
-      rej = circle_reject_shift(rej, rq.x, rq.y, rq.z, cx.x, cy.x, cr.x);
-      rej = circle_reject_shift(rej, rq.x, rq.y, rq.z, cx.y, cy.y, cr.y);
-      rej = circle_reject_shift(rej, rq.x, rq.y, rq.z, cx.z, cy.z, cr.z);
-      rej = circle_reject_shift(rej, rq.x, rq.y, rq.z, cx.w, cy.w, cr.w);
+      {   // four circle tests as two packed passes (columns x|y, z|w against the broadcast row)
+        const unsigned long long X1 = f2_pack(rq.x, rq.x), Y1 = f2_pack(rq.y, rq.y), Q1 = f2_pack(rq.z, rq.z);
+        float t0, t1, t2, t3;
+        circle_t2(X1, Y1, Q1, f2_pack(cx.x, cx.y), f2_pack(cy.x, cy.y), f2_pack(cr.x, cr.y), t0, t1);
+        circle_t2(X1, Y1, Q1, f2_pack(cx.z, cx.w), f2_pack(cy.z, cy.w), f2_pack(cr.z, cr.w), t2, t3);
+        rej = __funnelshift_l(__float_as_uint(t0), rej, 1);
+        rej = __funnelshift_l(__float_as_uint(t1), rej, 1);
+        rej = __funnelshift_l(__float_as_uint(t2), rej, 1);
+        rej = __funnelshift_l(__float_as_uint(t3), rej, 1);
+      }
       if (k < rows_left) {
         if (VEC4) {
           if (gc < n2) st_stream_v4(o, 0.f, 0.f, 0.f, 0.f);   // n2 % 4 == 0 => all four in range
@@ -273,7 +279,7 @@ JDET_API int jdet_box_iou_rotated_ex(const float* boxes1, int n1, const float* b
   dim3 grid(jdet_ceil_div(n2, kTC), jdet_ceil_div(n1, kTR));
   const bool vec = (n2 % 4 == 0) && (((uintptr_t)ious & 15) == 0);
   const long long pairs = (long long)n1 * n2;
-  const int xgrid = (int)(pairs < 256 * 1024 ? (pairs + 255) / 256 : kNumSMs * 8);
+  const int xgrid = (int)(pairs < 256 * 1024 ? (pairs + 255) / 256 : num_sms() * 8);
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(iou_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExactSmem));
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(iou_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExactSmem));
   if (version == 0) {

@@ -22,7 +22,20 @@ static inline int jdet_ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 namespace jdet {
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs (compile-time default; launch sizing asks the device: num_sms())
+
+// SM count of the current device, cached per device (grid sizing of the persistent kernels)
+inline int num_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 

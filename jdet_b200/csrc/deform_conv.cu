@@ -302,7 +302,7 @@ JDET_API int jdet_deform_im2col(const float* x, const float* offset, int B, int 
   if (e) return e;
   if (B == 0) return 0;
   if (!x || !offset || !columns) return JDET_ERR_BAD_ARG;
-  jdet::deform_im2col_kernel<<<jdet::kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(x, offset, s, columns);
+  jdet::deform_im2col_kernel<<<jdet::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(x, offset, s, columns);
   return (int)cudaGetLastError();
 }
 
@@ -316,7 +316,7 @@ JDET_API int jdet_deform_col2im(const float* col_grad, const float* offset, int 
   if (B == 0) return 0;
   if (!col_grad || !offset || !grad_x) return JDET_ERR_BAD_ARG;
   JDET_RETURN_IF_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)B * C * H * W * 4, (cudaStream_t)stream));
-  jdet::deform_col2im_kernel<<<jdet::kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(col_grad, offset, s, grad_x);
+  jdet::deform_col2im_kernel<<<jdet::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(col_grad, offset, s, grad_x);
   return (int)cudaGetLastError();
 }
 
@@ -329,6 +329,6 @@ JDET_API int jdet_deform_col2im_coord(const float* col_grad, const float* x, con
   if (e) return e;
   if (B == 0) return 0;
   if (!col_grad || !x || !offset || !grad_offset) return JDET_ERR_BAD_ARG;
-  jdet::deform_col2im_coord_kernel<<<jdet::kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(col_grad, x, offset, s, grad_offset);
+  jdet::deform_col2im_coord_kernel<<<jdet::num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(col_grad, x, offset, s, grad_offset);
   return (int)cudaGetLastError();
 }

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(kMaskThreads, JDET_NMS_MASK_MINB) nms_mask_ker
     uint4* __restrict__ xqueue, int xcap) {
   const int label_in_pair = flags & 1;       // thr < 0 corner: single segment, label mismatch => IoU 0
   const bool cpu_arith = (flags & 2) != 0;   // the reference CPU build's hull sort; no IoU-upper-bound pruning (its IoU is not bounded by the true one)
+  const bool no_prune = (flags & 4) != 0;               // JDET_NMS_NO_PRUNE=1 (tests): every SAT survivor takes the exact routine
   extern __shared__ __align__(16) unsigned char s_dyn[];
   BoxRec* s_row = reinterpret_cast<BoxRec*>(s_dyn);                       //  2 KB
   BoxRec* s_col = s_row + 64;                                             // 16 KB
@@ -226,11 +227,15 @@ __global__ void __launch_bounds__(kMaskThreads, JDET_NMS_MASK_MINB) nms_mask_ker
       for (int j = 0; j < kColsPerThread; j++) { wlo[j] = 0u; whi[j] = 0u; }
 #pragma unroll
       for (int r = 0; r < 32; r++) {
+        // rows r and r + 32 against column j in one packed pass (FADD2 / FMUL2 / FFMA2: 4 issue slots per pair, not 7)
         const float4 ra = s_rowq[r], rb2 = s_rowq[r + 32];
+        const unsigned long long X1 = f2_pack(ra.x, rb2.x), Y1 = f2_pack(ra.y, rb2.y), Q1 = f2_pack(ra.z, rb2.z);
 #pragma unroll
         for (int j = 0; j < kColsPerThread; j++) {
-          wlo[j] = circle_reject_shift(wlo[j], ra.x, ra.y, ra.z, cx[j], cy[j], cq[j]);
-          whi[j] = circle_reject_shift(whi[j], rb2.x, rb2.y, rb2.z, cx[j], cy[j], cq[j]);
+          float ta, tb;
+          circle_t2(X1, Y1, Q1, f2_pack(cx[j], cx[j]), f2_pack(cy[j], cy[j]), f2_pack(cq[j], cq[j]), ta, tb);
+          wlo[j] = __funnelshift_l(__float_as_uint(ta), wlo[j], 1);
+          whi[j] = __funnelshift_l(__float_as_uint(tb), whi[j], 1);
         }
       }
 #pragma unroll
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(kMaskThreads, JDET_NMS_MASK_MINB) nms_mask_ker
           const BoxRec& A = s_row[(e >> 6) & 63];
           const BoxRec& B = s_col[(e >> 12) * 64 + (e & 63)];
           // SAT reject, then the IoU upper bound: a pair that provably cannot exceed thr never reaches phase 3
-          keep = label_in_pair ? true : (A.tag == B.tag && !sat_disjoint<0>(A, B) && (cpu_arith || !(iou_upper_bound<0>(A, B) < thr)));
+          keep = label_in_pair ? true : (A.tag == B.tag && !sat_disjoint<0>(A, B) && (cpu_arith || no_prune || !(iou_upper_bound<0>(A, B) < thr)));
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (bal) {
@@ -499,7 +504,7 @@ JDET_API int jdet_nms_rotated_ex(const float* dets, int n, int box_length, const
   cudaStream_t st = (cudaStream_t)stream;
   const int T = 256, G = jdet_ceil_div(n + 1, T);
   const int label_in_pair = (iou_threshold < 0.f) ? 1 : 0;   // cross-class pairs then DO suppress (0 > thr)
-  const int flags = label_in_pair | (convention == 0 ? 2 : 0);
+  const int flags = label_in_pair | (convention == 0 ? 2 : 0) | (getenv("JDET_NMS_NO_PRUNE") ? 4 : 0);
   const bool segment = (box_length == 6) && !label_in_pair;
 
   JDET_RETURN_IF_CUDA(cudaMemsetAsync(keep, 0, (size_t)n, st));
@@ -534,16 +539,16 @@ JDET_API int jdet_nms_rotated_ex(const float* dets, int n, int box_length, const
   }
   const size_t mask_smem = (size_t)(64 + kCH * 64) * sizeof(BoxRec) + 64 * 16 + (size_t)kCH * 64 * 2 * 4 + (size_t)kQCap * 2 * 2;
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mask_smem));
-  nms_mask_kernel<<<kNumSMs * JDET_NMS_MASK_MINB, kMaskThreads, mask_smem, st>>>(w.rec, w.seg_start, w.item_base, w.tile_base,
+  nms_mask_kernel<<<num_sms() * JDET_NMS_MASK_MINB, kMaskThreads, mask_smem, st>>>(w.rec, w.seg_start, w.item_base, w.tile_base,
                                                         w.flag_scan, n, iou_threshold, flags,
                                                         w.counters, w.mask, w.xqueue, w.xcap);
   const size_t exact_smem = (size_t)3 * kExactCap * 256 * sizeof(float);
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem));
-  nms_exact_kernel<<<kNumSMs * 8, 256, exact_smem, st>>>(w.rec, w.counters, w.xqueue, w.xcap, iou_threshold, flags, w.mask);
+  nms_exact_kernel<<<num_sms() * 8, 256, exact_smem, st>>>(w.rec, w.counters, w.xqueue, w.xcap, iou_threshold, flags, w.mask);
   const size_t smem = (size_t)jdet_ceil_div(n, 64) * 8;
   if (smem > 48 * 1024)
     JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nms_scan_kernel<<<kNumSMs, kScanThreads, smem, st>>>(w.seg_start, w.tile_base, w.flag_scan, n, w.sorted_idx,
+  nms_scan_kernel<<<num_sms(), kScanThreads, smem, st>>>(w.seg_start, w.tile_base, w.flag_scan, n, w.sorted_idx,
                                                        w.mask, keep);
   return (int)cudaGetLastError();
 }
@@ -554,7 +559,9 @@ namespace jdet {
 __global__ void score_key_kernel(const float* __restrict__ s, int n, unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  unsigned u = __float_as_uint(s[i]);
+  float v = s[i];
+  if (v == 0.f) v = 0.f;                             // -0.0 and +0.0 are one score: ties go to the lower index
+  unsigned u = __float_as_uint(v);
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // ascending-orderable
   keys[i] = ~u;                                      // descending
   vals[i] = i;

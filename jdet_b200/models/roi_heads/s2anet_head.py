@@ -103,15 +103,17 @@ class AlignConv(nn.Module):
     execute = forward
 
 
-class _ConvReLU(nn.Sequential):
-    """ConvModule(conv 3x3 + ReLU) as S2ANet builds it (no norm)."""
+class _ConvReLU(nn.Module):
+    """ConvModule(conv 3x3 + ReLU) as S2ANet builds it (models/utils/modules.py:93-190, no norm): the same attribute
+    names (`conv`, `activate`), so a reference checkpoint's keys (`fam_reg_convs.0.conv.weight`, ...) load as they are."""
 
     def __init__(self, cin, cout):
-        super().__init__(nn.Conv2d(cin, cout, 3, stride=1, padding=1), nn.ReLU())
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 3, stride=1, padding=1)
+        self.activate = nn.ReLU()
 
-    @property
-    def conv(self):
-        return self[0]
+    def forward(self, x):
+        return self.activate(self.conv(x))
 
 
 class S2ANetHead(nn.Module):
@@ -186,7 +188,9 @@ class S2ANetHead(nn.Module):
         return fam_bbox_pred, refine_anchor, self.odm_cls(cls_feat), self.odm_reg(reg_feat)
 
     @torch.no_grad()
-    def get_bboxes_single(self, cls_score_list, bbox_pred_list, mlvl_anchors, cfg=None):
+    def get_bboxes_single(self, cls_score_list, bbox_pred_list, mlvl_anchors, cfg=None, scale_factor=1.0, rescale=True):
+        """s2anet_head.py:543-601; `rescale` divides the boxes' x, y, w, h by scale_factor before NMS (:585-586; get_bboxes
+        defaults to rescale=True, :517), so detections come back in original-image coordinates."""
         from ...ops.nms_rotated import multiclass_nms_rotated
         from ..boxes.box_ops import delta2bbox_rotated, rotated_box_to_poly
         cfg = self.test_cfg if cfg is None else cfg
@@ -202,18 +206,24 @@ class S2ANetHead(nn.Module):
             mlvl_bboxes.append(delta2bbox_rotated(anchors, bbox_pred, self.target_means, self.target_stds))
             mlvl_scores.append(scores)
         mlvl_bboxes, mlvl_scores = torch.cat(mlvl_bboxes), torch.cat(mlvl_scores)
+        if rescale:
+            mlvl_bboxes = mlvl_bboxes.clone()
+            mlvl_bboxes[..., :4] /= scale_factor
         mlvl_scores = torch.cat([mlvl_scores.new_zeros((mlvl_scores.shape[0], 1)), mlvl_scores], dim=1)
         det_bboxes, det_labels = multiclass_nms_rotated(mlvl_bboxes, mlvl_scores, cfg['score_thr'], cfg['nms'], cfg['max_per_img'])
         return rotated_box_to_poly(det_bboxes[:, :5]), det_bboxes[:, 5], det_labels
 
     @torch.no_grad()
-    def forward(self, feats):
-        """feats: list of (N,C,H_l,W_l) FPN maps -> list over images of (polys (k,8), scores (k,), labels (k,))."""
+    def forward(self, feats, img_metas=None, rescale=True):
+        """feats: list of (N,C,H_l,W_l) FPN maps -> list over images of (polys (k,8), scores (k,), labels (k,)).
+        img_metas (optional): per image a dict with 'scale_factor' (default 1.0), as the reference's get_bboxes reads it."""
         outs = [self.forward_single(x, s) for x, s in zip(feats, self.anchor_strides)]
         num_imgs = feats[0].shape[0]
         results = []
         for i in range(num_imgs):
-            results.append(self.get_bboxes_single([o[2][i] for o in outs], [o[3][i] for o in outs], [o[1][i] for o in outs]))
+            sf = 1.0 if img_metas is None else img_metas[i].get('scale_factor', 1.0)
+            results.append(self.get_bboxes_single([o[2][i] for o in outs], [o[3][i] for o in outs], [o[1][i] for o in outs],
+                                                  scale_factor=sf, rescale=rescale))
         return results
 
     execute = forward

@@ -120,6 +120,10 @@ class RotationInvariantPooling(nn.Module):
         super().__init__()
         self.nInputPlane = nInputPlane
         self.nOrientation = nOrientation
+        # the reference keeps an unused Conv2d + BatchNorm2d here (orn.py:600-606, "TODO remove this"; its call is commented
+        # out, :612-614); the parameters exist in reference checkpoints (`or_pool.conv.*`), so they exist here too
+        hidden = int(nInputPlane / nOrientation)
+        self.conv = nn.Sequential(nn.Conv2d(hidden, nInputPlane, 1, 1), nn.BatchNorm2d(nInputPlane))
 
     def forward(self, x):
         N, c, h, w = x.shape

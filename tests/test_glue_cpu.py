@@ -83,3 +83,30 @@ def test_iou_poly_restatement_known_answers():
     want = oracle.box_iou_rotated(b, b, 0, oracle.VARIANT_CUDA)
     got = np.array([[glue.iou_poly(polys[i], polys[j]) for j in range(40)] for i in range(40)])
     assert np.abs(got - want).max() < 2e-5                                           # float32 corners vs the fp32 rectangle routine
+
+
+def test_s2anet_head_state_dict_keys_match_reference_names():
+    """A reference S2ANetHead checkpoint names its ConvModule parameters `<list>.<i>.conv.{weight,bias}` and carries the unused
+    `or_pool.conv.*` (Conv2d + BatchNorm2d); the mirror must use the same keys so such a checkpoint loads as it is."""
+    from jdet_b200.models.roi_heads.s2anet_head import S2ANetHead
+    head = S2ANetHead(16, 256)
+    keys = set(head.state_dict().keys())
+    want = set()
+    for lst in ("fam_reg_convs", "odm_reg_convs", "odm_cls_convs"):
+        for i in range(2):
+            want |= {"%s.%d.conv.weight" % (lst, i), "%s.%d.conv.bias" % (lst, i)}
+    want |= {"fam_reg.weight", "fam_reg.bias", "align_conv.deform_conv.weight", "or_conv.weight", "or_conv.bias",
+             "odm_cls.weight", "odm_cls.bias", "odm_reg.weight", "odm_reg.bias",
+             "or_pool.conv.0.weight", "or_pool.conv.0.bias", "or_pool.conv.1.weight", "or_pool.conv.1.bias",
+             "or_pool.conv.1.running_mean", "or_pool.conv.1.running_var"}
+    assert want <= keys, sorted(want - keys)
+    extra = {k for k in keys - want if not k.endswith("num_batches_tracked") and k != "or_conv.indices"}
+    assert not extra, sorted(extra)
+    assert tuple(head.state_dict()["or_conv.weight"].shape) == (32, 256, 1, 3, 3)
+
+
+def test_argsort_key_treats_signed_zero_as_one_score():
+    """documented tie rule of jdet_argsort_desc (lower index first) — the host-side statement of it, for the CPU suite"""
+    s = np.array([0.0, -0.0, 0.5, -0.0, 0.0], np.float32)
+    order = np.argsort(-np.where(s == 0, 0.0, s), kind="stable")
+    assert order.tolist() == [2, 0, 1, 3, 4]

@@ -1068,3 +1068,48 @@ def test_horizontal_nms_matches_torchvision():
     got = horizontal_nms(hbb, sc, grp, 0.7)
     want = nms(hbb + (grp.float() * 2000)[:, None], sc, 0.7)
     assert torch.equal(got, want)
+
+
+def test_argsort_desc_signed_zero_ties_and_rescale():
+    s = cu(np.array([0.0, -0.0, 0.5, -0.0, 0.0, -1.0], np.float32))
+    assert ops().nms_rotated.argsort_desc(s).cpu().numpy().tolist() == [2, 0, 1, 3, 4, 5]
+
+
+@pytest.mark.parametrize("kind", ["clustered", "lattice", "big"])
+def test_nms_pruning_bound_never_changes_the_mask(kind, monkeypatch):
+    """ADVICE: the IoU-upper-bound pruning of the mask kernel assumes reference IoU <= bound.  JDET_NMS_NO_PRUNE=1 sends every
+    SAT survivor through the exact routine; the keep masks must be identical with and without pruning."""
+    rng = np.random.default_rng(5)
+    if kind == "lattice":
+        n = 3000
+        d = _lattice_boxes(rng, n)
+    else:
+        n = 100000 if kind == "big" else 20000
+        d = np.concatenate([clustered_boxes(rng, n // 2, 50), dota_boxes(rng, n - n // 2)])
+    s, l = tie_free_scores(rng, n), rng.integers(0, 15 if kind != "lattice" else 2, n)
+    d6 = cu(np.concatenate([d, l[:, None].astype(np.float32)], 1))
+    order = ops().nms_rotated.argsort_desc(cu(s))
+    for thr in (0.1, 0.5):
+        monkeypatch.delenv("JDET_NMS_NO_PRUNE", raising=False)
+        a = ops().nms_rotated.nms_rotated_cuda(d6, order, thr, 6)
+        monkeypatch.setenv("JDET_NMS_NO_PRUNE", "1")
+        b = ops().nms_rotated.nms_rotated_cuda(d6, order, thr, 6)
+        assert torch.equal(a, b)
+
+
+def test_candidate_queue_full_path(monkeypatch):
+    """ADVICE: the device-wide candidate queues of IoU and NMS (now 64-bit reservation counters) fall back to in-CTA
+    evaluation when full.  JDET_TEST_QUEUE_CAP forces that path on a dense cluster; results must not change."""
+    rng = np.random.default_rng(2)
+    b = clustered_boxes(rng, 1500, 200, 300.0)
+    l = rng.integers(0, 3, b.shape[0])
+    d6 = cu(np.concatenate([b, l[:, None].astype(np.float32)], 1))
+    order = ops().nms_rotated.argsort_desc(cu(tie_free_scores(rng, b.shape[0])))
+    monkeypatch.delenv("JDET_TEST_QUEUE_CAP", raising=False)
+    iou0 = ops().box_iou_rotated(cu(b), cu(b[:700]))
+    keep0 = ops().nms_rotated.nms_rotated_cuda(d6, order, 0.3, 6)
+    monkeypatch.setenv("JDET_TEST_QUEUE_CAP", "1000")
+    iou1 = ops().box_iou_rotated(cu(b), cu(b[:700]))
+    keep1 = ops().nms_rotated.nms_rotated_cuda(d6, order, 0.3, 6)
+    assert torch.equal(keep0, keep1)
+    assert np.array_equal(bits(iou0.cpu().numpy()), bits(iou1.cpu().numpy()))
