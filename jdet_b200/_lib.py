@@ -101,6 +101,8 @@ def lib():
                 raise RuntimeError("JDET_B200_LIB=%s does not exist" % alt)
             L = ctypes.CDLL(alt)
             for name, (res, args) in SIGNATURES.items():
+                if not hasattr(L, name):       # an older build under A/B: entry points added since are simply absent
+                    continue
                 fn = getattr(L, name)
                 fn.restype = res
                 fn.argtypes = args

@@ -286,7 +286,8 @@ __device__ __forceinline__ void relayout_tile_v4(const float* __restrict__ in, f
 // grid = (tiles_x + tables_per_row, tiles_y * B): in every grid row the first tiles_x CTAs transpose a tile, the
 // rest build tables (tables_per_row = ceil(R / rows)), so both kinds of work are in flight throughout and no
 // index needs a division.  tiles_x == 0: tables only (channel-last input).
-template <int VERSION>
+// STAGED: the opt-in TMA path (packed taps, chunk_record); false compiles the plain LSU-table build only
+template <int VERSION, bool STAGED>
 __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restrict__ in, float* __restrict__ nhwc, int C, int H,
                                                             int W, int tiles_x, int tiles_y, const float* __restrict__ rois,
                                                             unsigned R, int PH, int PW, int sample_num,
@@ -333,21 +334,23 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
   g4::ChunkScratch* scratch = reinterpret_cast<g4::ChunkScratch*>(raw + nbins * tpb);
   if (threadIdx.x == 0) hdr[0] = make_int4(g.batch, __float_as_int(g.inv_count), fstride, level);
   const int Hl = L.lv[level].H, Wl = L.lv[level].W;
-  if (pcap > 0) build_tap_table<VERSION, true>(g, nbins, PW, Hl, Wl, raw, fin, fstride, cnt);     // entries: ((y << 16) | x, weight)
+  if constexpr (STAGED) build_tap_table<VERSION, true>(g, nbins, PW, Hl, Wl, raw, fin, fstride, cnt);     // entries: ((y << 16) | x, weight)
   else build_tap_table<VERSION, false>(g, nbins, PW, Hl, Wl, raw, fin, fstride, cnt, 4u * (unsigned)C);   // LSU path only: byte offsets at once
   // One staged chunk (roi_gather_tma.cuh) when the RoI's distinct pixels fit pcap — guess first from the geometry, distinct
   // pixels ~ area + 1.5 * (w + h) of the scaled box (cfg2 at 128 pixels: 3 wasted attempts, 15 missed of 2048) —, else the
   // LSU-path record: entries become byte offsets into one image of the channel-last map.
-  const float rw = g.bin_w * (float)PW, rh = g.bin_h * (float)PH;
   int bytes = RL.cnpx_off;
   bool staged = false;
-  if (rw * rh + 1.5f * (rw + rh) + 2.f <= (float)pcap)
-    staged = g4::chunk_record(smem, nbins, fstride, tpb, pcap, pxbytes, Wl, g.batch * Hl * Wl, *scratch, &bytes);
-  if (!staged && pcap > 0) {
-    const unsigned px4c = 4u * (unsigned)C;
-    for (int e = threadIdx.x; e < nbins * fstride; e += blockDim.x) {
-      const int p = fin[e].x;
-      fin[e].x = (int)((unsigned)((p >> 16) * Wl + (p & 0xffff)) * px4c);
+  if constexpr (STAGED) {
+    const float rw = g.bin_w * (float)PW, rh = g.bin_h * (float)PH;
+    if (rw * rh + 1.5f * (rw + rh) + 2.f <= (float)pcap)
+      staged = g4::chunk_record(smem, nbins, fstride, tpb, pcap, pxbytes, Wl, g.batch * Hl * Wl, *scratch, &bytes);
+    if (!staged) {
+      const unsigned px4c = 4u * (unsigned)C;
+      for (int e = threadIdx.x; e < nbins * fstride; e += blockDim.x) {
+        const int p = fin[e].x;
+        fin[e].x = (int)((unsigned)((p >> 16) * Wl + (p & 0xffff)) * px4c);
+      }
     }
   }
   if (!staged) {
@@ -356,7 +359,9 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
   }
   int4* dst = reinterpret_cast<int4*>(tables + (size_t)idx * (size_t)rec_pitch);
   for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = hdr[i];
-  if (threadIdx.x == 0) work_counter[64 + (size_t)(kRoiBuckets + 1) * R + idx] = bytes;
+  if constexpr (STAGED) {
+    if (threadIdx.x == 0) work_counter[64 + (size_t)(kRoiBuckets + 1) * R + idx] = bytes;
+  }
   if (staged) {
     if (threadIdx.x == 0) work_counter[64 + (size_t)kRoiBuckets * R + atomicAdd(work_counter + 2, 1)] = (int)idx;
     return;
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
 template <int QL, bool PAIR>
 __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __grid_constant__ RoiLevels L,
                                                              const unsigned char* __restrict__ tables, size_t stride, int C,
-                                                             int nbins, int nslabs, int R, uint32_t rec_bytes, int fin_off,
+                                                             int nbins, int nslabs, int R, uint32_t rec_bytes, int fin_off, int items_known,
                                                              int* __restrict__ work_counter, float* __restrict__ out) {
   constexpr int SLAB = PAIR ? 8 * QL : 4 * QL;                      // PAIR: a lane owns two channel quads 4*QL apart
   extern __shared__ __align__(128) unsigned char smem[];
@@ -404,10 +409,13 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
   // NEXT item is fetched by a bulk-async copy while the current one is gathered, and the slab store of the
   // PREVIOUS item drains while the current one runs — a CTA never sits waiting for its 6.7 KB table or its store.
   int cur = blockIdx.x;                                            // first item: static; later ones from the counter
-  int items = 0;                                                   // RoIs the prologue left to this path = the LPT buckets
+  int items = items_known;                                         // >= 0: every RoI takes this path (nothing staged): known on the host
+  if (items < 0) {                                                 // else the RoIs the prologue left to this path = the LPT buckets
+    items = 0;
 #pragma unroll
-  for (int b = 0; b < kRoiBuckets; b++) items += work_counter[16 + b];
-  items *= nslabs;
+    for (int b = 0; b < kRoiBuckets; b++) items += work_counter[16 + b];
+    items *= nslabs;
+  }
   __shared__ int s_roi[2];                                         // RoI of the item whose table sits in rec buffer 0 / 1
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
@@ -501,8 +509,15 @@ __global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __g
     g4::fma2(a.x, a.y, w2, v[i0 + 4].x, v[i0 + 4].y); g4::fma2(a.z, a.w, w2, v[i0 + 4].z, v[i0 + 4].w);                 \
     g4::fma2(a.x, a.y, w3, v[i0 + 6].x, v[i0 + 6].y); g4::fma2(a.z, a.w, w3, v[i0 + 6].z, v[i0 + 6].w);                 \
   } while (0)
+#ifdef JDET_ROI_SCALAR_FMA   // A/B switch (tools/ab_libs.py): the round-1 scalar chain
+#define JDET_ACC1(a, c, i0) a.c = fmaf(w3, v[i0 + 6].c, fmaf(w2, v[i0 + 4].c, fmaf(w1, v[i0 + 2].c, fmaf(w0, v[i0].c, a.c))))
+        JDET_ACC1(acc0, x, 0); JDET_ACC1(acc0, y, 0); JDET_ACC1(acc0, z, 0); JDET_ACC1(acc0, w, 0);
+        JDET_ACC1(acc1, x, 1); JDET_ACC1(acc1, y, 1); JDET_ACC1(acc1, z, 1); JDET_ACC1(acc1, w, 1);
+#undef JDET_ACC1
+#else
         JDET_ACC(acc0, 0);
         JDET_ACC(acc1, 1);
+#endif
 #undef JDET_ACC
       }
       if (valid) {
@@ -844,13 +859,15 @@ static cudaError_t launch_prologue(int version, const float* input_nchw, float* 
   dim3 pgrid(tiles_x + jdet_ceil_div(Rt, rows), rows);
   const size_t smem = std::max(cfg.stride + (size_t)nbins * sampling_ratio * sampling_ratio * 4 * sizeof(int2) + sizeof(g4::ChunkScratch) + 16,
                                sizeof(float) * 32 * (kTileW + 1));
-  if (version == 1) {
-    if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-    roi_prologue_kernel<1><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, roi_tma_enabled() ? cfg.pcap : 0, cfg.pxbytes, (int)cfg.stride, L);
-  } else {
-    if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; }
-    roi_prologue_kernel<0><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, roi_tma_enabled() ? cfg.pcap : 0, cfg.pxbytes, (int)cfg.stride, L);
-  }
+  const bool tma = roi_tma_enabled();
+#define JDET_LAUNCH_PRO(V, S)                                                                                          \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_prologue_kernel<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; } \
+    roi_prologue_kernel<V, S><<<pgrid, 256, smem, st>>>(input_nchw, nhwc_scratch, C, H, W, tiles_x, tiles_y, rois, (unsigned)Rt, PH, PW, sampling_ratio, tables, vec, work_counter, tma ? cfg.pcap : 0, cfg.pxbytes, (int)cfg.stride, L); \
+  } while (0)
+  if (version == 1) { if (tma) JDET_LAUNCH_PRO(1, true); else JDET_LAUNCH_PRO(1, false); }
+  else              { if (tma) JDET_LAUNCH_PRO(0, true); else JDET_LAUNCH_PRO(0, false); }
+#undef JDET_LAUNCH_PRO
   return cudaGetLastError();
 }
 
@@ -903,7 +920,7 @@ static cudaError_t launch_gather(const RoiLevels& L, int B, const unsigned char*
 #define JDET_LAUNCH_ROI(QL_, PAIR_)                                                                                    \
   do {                                                                                                                 \
     if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_gather_kernel<QL_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; } \
-    roi_gather_kernel<QL_, PAIR_><<<lgrid, 256, smem, st>>>(L, tables, cfg.stride, C, nbins, nslabs, R, rec_bytes, RL.fin_off, work_counter, output); \
+    roi_gather_kernel<QL_, PAIR_><<<lgrid, 256, smem, st>>>(L, tables, cfg.stride, C, nbins, nslabs, R, rec_bytes, RL.fin_off, roi_tma_enabled() ? -1 : R * nslabs, work_counter, output); \
   } while (0)
   if (pair) JDET_LAUNCH_ROI(16, true); else JDET_LAUNCH_ROI(16, false);
 #undef JDET_LAUNCH_ROI
