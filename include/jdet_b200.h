@@ -179,6 +179,15 @@ int jdet_align_conv_forward(const float* x, const float* anchors, const float* w
                             int W, int Co, float stride, float* out, void* workspace, size_t workspace_bytes,
                             void* stream);
 
+/* the same for every FPN level of one head in ONE call: S2ANetHead applies its AlignConv to 5 levels (s2anet_head.py:230-237);
+ * one persistent tcgen05 launch covers all levels' tiles (the 4 / 16 / 64 tiles of the coarse levels fill the last wave
+ * instead of costing a launch each) and the weight is split once.  xs / anchors / outs / Hs / Ws / strides: HOST arrays of
+ * nlevels (<= 8) entries.  tcgen05 shape class only (else JDET_ERR_UNSUPPORTED: loop over jdet_align_conv_forward).       */
+size_t jdet_align_conv_forward_multi_workspace_bytes(int nlevels, int N, int C, const int* Hs, const int* Ws, int Co);
+int jdet_align_conv_forward_multi(const float* const* xs, const float* const* anchors, const float* weight, int nlevels,
+                                  int N, int C, const int* Hs, const int* Ws, int Co, const float* strides,
+                                  float* const* outs, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@ SIGNATURES = {
     "jdet_deform_col2im_coord": (_i, [_p, _p, _p] + [_i] * 13 + [_p, _p]),
     "jdet_align_conv_forward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "jdet_align_conv_forward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _sz, _p]),
+    "jdet_align_conv_forward_multi_workspace_bytes": (_sz, [_i, _i, _i, _p, _p, _i]),
+    "jdet_align_conv_forward_multi": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _sz, _p]),
 }
 
 

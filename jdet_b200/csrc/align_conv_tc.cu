@@ -103,16 +103,32 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // 16-B chunk j of row r lives at chunk (j ^ ((r >> 1) & 3))  (Swizzle<2,4,3> on byte addresses)
 __device__ __host__ __forceinline__ int swz_chunk(int r, int j) { return j ^ ((r >> 1) & 3); }
 
-struct Params {
+constexpr int kMaxLevels = 8;
+// One launch covers every FPN level of a head (S2ANet: 5): tiles are numbered level after level, so the 4 / 16 / 64 tiles
+// of the coarse levels fill the tail of the last wave instead of costing a launch (and a mostly empty wave) each.
+struct Level {
   const float* x_nhwc;      // (N, H, W, C)
   const float* anchors;     // (N, H, W, 5)
-  const float* b_hi;        // [K/32][Co][32] swizzled
-  const float* b_lo;
   float* out;               // (N, Co, H, W)
-  int N, C, H, W, Co;
+  int H, W;
   float stride;
+  int tile_begin;           // first tile of this level
+};
+struct Params {
+  Level lv[kMaxLevels];
+  int nlevels;
+  const float* b_hi;        // [K/16][Co][16] swizzled (shared by the levels: one weight)
+  const float* b_lo;
+  int N, C, Co;
   int num_tiles;
 };
+__device__ __forceinline__ int level_of(const Params& p, int tile) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxLevels; i++)
+    if (i < p.nlevels && tile >= p.lv[i].tile_begin) l = i;
+  return l;
+}
 
 // weight (Co, C, 3, 3) -> hi/lo [kb][co][16] with kb = tap*(C/16) + c/16, 16-B chunks swizzled like the smem rows
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, int Co, int C, float* __restrict__ hi,
@@ -133,7 +149,7 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
   lo[dst] = l;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.Co * kRowBytes;
@@ -150,8 +166,6 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HW = p.H * p.W;
-  const long long P = (long long)p.N * HW;
   const int cblocks = p.C / kBlockK;
   const int num_kb = 9 * cblocks;
 
@@ -174,21 +188,25 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
     const int pw = warp - 4, sp = lane / kQuads, q = lane % kQuads;
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const Level& L = p.lv[level_of(p, tile)];
+      const int HW = L.H * L.W;
+      const long long P = (long long)p.N * HW;
+      const int ltile = tile - L.tile_begin;
       // per-pixel anchor geometry (s2anet_head.py:689-698), 8 pixels per lane
       float gx[kPix], gy[kPix], gdw[kPix], gdh[kPix], gc[kPix], gs[kPix], fh[kPix], fw[kPix];
       long long pbase[kPix];          // n * HW (pixel index of the image origin), -1 => row beyond the tensor
 #pragma unroll
       for (int it = 0; it < kPix; it++) {
         const int r = pw * (kPixPerStep * kPix) + it * kPixPerStep + sp;
-        const long long pix = (long long)tile * kBlockM + r;
+        const long long pix = (long long)ltile * kBlockM + r;
         if (pix < P) {
           const int n = (int)(pix / HW), hw = (int)(pix - (long long)n * HW);
-          const int h = hw / p.W, w = hw - h * p.W;
-          const float* a = p.anchors + pix * 5;
-          gx[it] = __fdiv_rn(__ldg(a + 0), p.stride);
-          gy[it] = __fdiv_rn(__ldg(a + 1), p.stride);
-          gdw[it] = __fdiv_rn(__fdiv_rn(__ldg(a + 2), p.stride), 3.f);
-          gdh[it] = __fdiv_rn(__fdiv_rn(__ldg(a + 3), p.stride), 3.f);
+          const int h = hw / L.W, w = hw - h * L.W;
+          const float* a = L.anchors + pix * 5;
+          gx[it] = __fdiv_rn(__ldg(a + 0), L.stride);
+          gy[it] = __fdiv_rn(__ldg(a + 1), L.stride);
+          gdw[it] = __fdiv_rn(__fdiv_rn(__ldg(a + 2), L.stride), 3.f);
+          gdh[it] = __fdiv_rn(__fdiv_rn(__ldg(a + 3), L.stride), 3.f);
           const float ang = __ldg(a + 4);
           gc[it] = cosf(ang);
           gs[it] = sinf(ang);
@@ -216,16 +234,16 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
           const float h_im = __fadd_rn(chh, __fsub_rn(ya, chh));
           o00[it] = o01[it] = o10[it] = o11[it] = -1;
           w1[it] = w2[it] = w3[it] = w4[it] = 0.f;
-          if (pbase[it] >= 0 && h_im > -1.f && w_im > -1.f && h_im < (float)p.H && w_im < (float)p.W) {
+          if (pbase[it] >= 0 && h_im > -1.f && w_im > -1.f && h_im < (float)L.H && w_im < (float)L.W) {
             const int hl = (int)floorf(h_im), wl = (int)floorf(w_im);
             const int hh = hl + 1, wh = wl + 1;
             const float lh = h_im - (float)hl, lw = w_im - (float)wl;
             const float uh = 1.f - lh, uw = 1.f - lw;
             w1[it] = uh * uw; w2[it] = uh * lw; w3[it] = lh * uw; w4[it] = lh * lw;
-            if (hl >= 0 && wl >= 0) o00[it] = hl * p.W + wl;
-            if (hl >= 0 && wh <= p.W - 1) o01[it] = hl * p.W + wh;
-            if (hh <= p.H - 1 && wl >= 0) o10[it] = hh * p.W + wl;
-            if (hh <= p.H - 1 && wh <= p.W - 1) o11[it] = hh * p.W + wh;
+            if (hl >= 0 && wl >= 0) o00[it] = hl * L.W + wl;
+            if (hl >= 0 && wh <= L.W - 1) o01[it] = hl * L.W + wh;
+            if (hh <= L.H - 1 && wl >= 0) o10[it] = hh * L.W + wl;
+            if (hh <= L.H - 1 && wh <= L.W - 1) o11[it] = hh * L.W + wh;
           }
         }
         for (int cb = 0; cb < cblocks; cb++) {
@@ -238,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 a = z, b = z, c = z, d = z;
             if (pbase[it] >= 0) {
-              const float* base = p.x_nhwc + (size_t)cb * kBlockK + q * 4;
+              const float* base = L.x_nhwc + (size_t)cb * kBlockK + q * 4;
               const size_t pb = (size_t)pbase[it];
               if (o00[it] >= 0) a = __ldg(reinterpret_cast<const float4*>(base + (pb + o00[it]) * p.C));
               if (o01[it] >= 0) b = __ldg(reinterpret_cast<const float4*>(base + (pb + o01[it]) * p.C));
@@ -319,12 +337,15 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      const Level& L = p.lv[level_of(p, tile)];
+      const int HW = L.H * L.W;
+      const long long P = (long long)p.N * HW;
       const int r = warp * 32 + lane;
-      const long long pix = (long long)tile * kBlockM + r;
+      const long long pix = (long long)(tile - L.tile_begin) * kBlockM + r;
       const bool ok = pix < P;
       const int n = ok ? (int)(pix / HW) : 0;
       const int hw = ok ? (int)(pix - (long long)n * HW) : 0;
-      float* obase = p.out + (size_t)n * p.Co * HW + hw;
+      float* obase = L.out + (size_t)n * p.Co * HW + hw;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (uint32_t)p.Co;
       for (int c0 = 0; c0 < p.Co; c0 += 32) {
         uint32_t v[32];
@@ -362,22 +383,36 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const Params
 
 bool align_conv_tc_supported(int C, int Co) { return C % tc::kBlockK == 0 && Co % 32 == 0 && Co >= 32 && Co <= 256; }
 
-size_t align_conv_tc_workspace_bytes(int N, int C, int H, int W, int Co) {
-  return jdet_align_up((size_t)N * C * H * W * 4, 1024) + 2 * jdet_align_up((size_t)Co * C * 9 * 4, 1024);
+size_t align_conv_tc_workspace_bytes_multi(int nlevels, int N, int C, const int* Hs, const int* Ws, int Co) {
+  size_t total = 2 * jdet_align_up((size_t)Co * C * 9 * 4, 1024);
+  for (int l = 0; l < nlevels; l++) total += jdet_align_up((size_t)N * C * Hs[l] * Ws[l] * 4, 1024);
+  return total;
 }
+size_t align_conv_tc_workspace_bytes(int N, int C, int H, int W, int Co) { return align_conv_tc_workspace_bytes_multi(1, N, C, &H, &W, Co); }
 
-int align_conv_tc_launch(const float* x, const float* anchors, const float* weight, int N, int C, int H, int W, int Co,
-                         float stride, float* out, void* workspace, cudaStream_t st) {
+// every level of one head in ONE persistent launch (the levels share the weight): re-layout per level, one weight split
+int align_conv_tc_launch_multi(const float* const* xs, const float* const* anchors, const float* weight, int nlevels, int N, int C,
+                               const int* Hs, const int* Ws, int Co, const float* strides, float* const* outs, void* workspace,
+                               cudaStream_t st) {
   using namespace tc;
-  float* x_nhwc = (float*)workspace;
-  float* b_hi = (float*)((char*)workspace + jdet_align_up((size_t)N * C * H * W * 4, 1024));
-  float* b_lo = (float*)((char*)b_hi + jdet_align_up((size_t)Co * C * 9 * 4, 1024));
-  launch_nchw_to_nhwc(x, x_nhwc, N, C, H * W, st);
+  if (nlevels < 1 || nlevels > kMaxLevels) return JDET_ERR_UNSUPPORTED;
+  char* wsp = (char*)workspace;
+  float* b_hi = (float*)wsp;   wsp += jdet_align_up((size_t)Co * C * 9 * 4, 1024);
+  float* b_lo = (float*)wsp;   wsp += jdet_align_up((size_t)Co * C * 9 * 4, 1024);
+  Params p{};
+  p.nlevels = nlevels; p.b_hi = b_hi; p.b_lo = b_lo; p.N = N; p.C = C; p.Co = Co;
+  long long tiles = 0;
+  for (int l = 0; l < nlevels; l++) {
+    float* x_nhwc = (float*)wsp;   wsp += jdet_align_up((size_t)N * C * Hs[l] * Ws[l] * 4, 1024);
+    launch_nchw_to_nhwc(xs[l], x_nhwc, N, C, Hs[l] * Ws[l], st);
+    p.lv[l] = Level{x_nhwc, anchors[l], outs[l], Hs[l], Ws[l], strides[l], (int)tiles};
+    tiles += ((long long)N * Hs[l] * Ws[l] + kBlockM - 1) / kBlockM;
+    if (tiles > 0x7fffffffLL) return JDET_ERR_UNSUPPORTED;
+  }
+  p.num_tiles = (int)tiles;
+  if (p.num_tiles == 0) return 0;
   const long long wt = (long long)Co * C * 9;
   weight_prep_kernel<<<(int)((wt + 255) / 256), 256, 0, st>>>(weight, Co, C, b_hi, b_lo);
-  Params p{x_nhwc, anchors, b_hi, b_lo, out, N, C, H, W, Co, stride, 0};
-  const long long P = (long long)N * H * W;
-  p.num_tiles = (int)((P + kBlockM - 1) / kBlockM);
   const size_t smem = 1024 + (size_t)kStages * (2 * kABytes + 2 * (size_t)Co * kRowBytes) + 256;
   cudaError_t e = cudaFuncSetAttribute(align_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -385,6 +420,11 @@ int align_conv_tc_launch(const float* x, const float* anchors, const float* weig
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   align_conv_tc_kernel<<<grid, kThreads, smem, st>>>(p);
   return (int)cudaGetLastError();
+}
+
+int align_conv_tc_launch(const float* x, const float* anchors, const float* weight, int N, int C, int H, int W, int Co,
+                         float stride, float* out, void* workspace, cudaStream_t st) {
+  return align_conv_tc_launch_multi(&x, &anchors, weight, 1, N, C, &H, &W, Co, &stride, &out, workspace, st);
 }
 
 }  // namespace jdet

@@ -86,6 +86,35 @@ class AlignConv(nn.Module):
                                             stream_ptr(xx.device)), "align_conv")
         return out
 
+    @torch.no_grad()
+    def forward_multi(self, xs, anchors_list, strides):
+        """The same AlignConv on every FPN level in ONE library call (inference): one persistent tcgen05 launch over all
+        levels' tiles, one weight split (jdet_align_conv_forward_multi).  xs[l] (N,C,H_l,W_l), anchors_list[l] (N,H_l,W_l,5).
+        Falls back to the per-level calls outside the fused shape class."""
+        import ctypes
+        dc = self.deform_conv
+        n = len(xs)
+        fused = self.kernel_size == 3 and dc.deformable_groups == 1 and dc.groups == 1
+        C, Co = xs[0].shape[1], dc.weight.shape[0]
+        if not fused or n > 8 or C % 16 != 0 or Co % 32 != 0 or Co > 256 or xs[0].shape[0] == 0:
+            return [self.forward(x, a, s) for x, a, s in zip(xs, anchors_list, strides)]
+        require_cuda(*xs, *anchors_list)
+        xx = [f32c(x) for x in xs]
+        aa = [f32c(a) for a in anchors_list]
+        w = f32c(dc.weight.detach())
+        N = xx[0].shape[0]
+        outs = [torch.empty((N, Co, x.shape[2], x.shape[3]), dtype=torch.float32, device=x.device) for x in xx]
+        arr = lambda vals, ct: (ct * n)(*vals)
+        Hs, Ws = arr([x.shape[2] for x in xx], ctypes.c_int), arr([x.shape[3] for x in xx], ctypes.c_int)
+        L = lib()
+        with torch.cuda.device(xx[0].device):
+            ws = scratch(L.jdet_align_conv_forward_multi_workspace_bytes(n, N, C, Hs, Ws, Co), xx[0].device)
+            check(L.jdet_align_conv_forward_multi(arr([x.data_ptr() for x in xx], ctypes.c_void_p), arr([a.data_ptr() for a in aa], ctypes.c_void_p),
+                                                  w.data_ptr(), n, N, C, Hs, Ws, Co, arr([float(s_) for s_ in strides], ctypes.c_float),
+                                                  arr([o.data_ptr() for o in outs], ctypes.c_void_p), ws.data_ptr(), ws.numel(),
+                                                  stream_ptr(xx[0].device)), "align_conv_multi")
+        return outs
+
     def forward(self, x, anchors, stride):
         """x (N,C,H,W), anchors (N,H,W,5) image space -> relu(deform_conv(x, offset(anchors)))."""
         require_cuda(x, anchors)
@@ -166,8 +195,7 @@ class S2ANetHead(nn.Module):
         nn.init.constant_(self.odm_cls.bias, bias_cls)
         self.align_conv.init_weights()
 
-    @torch.no_grad()
-    def forward_single(self, x, stride):
+    def _fam(self, x, stride):
         f = x
         for conv in self.fam_reg_convs:
             f = conv(f)
@@ -177,15 +205,31 @@ class S2ANetHead(nn.Module):
         key = (lvl, size, x.device)
         if key not in self.base_anchors:
             self.base_anchors[key] = self.anchor_generators[lvl].grid_anchors(size, stride, device=x.device)
-        refine_anchor = bbox_decode(fam_bbox_pred, self.base_anchors[key], self.target_means, self.target_stds)
-        align_feat = self.align_conv(x, refine_anchor, stride)
+        return fam_bbox_pred, bbox_decode(fam_bbox_pred, self.base_anchors[key], self.target_means, self.target_stds)
+
+    def _odm(self, align_feat):
         or_feat = self.or_conv(align_feat)
         reg_feat, cls_feat = or_feat, (self.or_pool(or_feat) if self.with_orconv else or_feat)
         for conv in self.odm_reg_convs:
             reg_feat = conv(reg_feat)
         for conv in self.odm_cls_convs:
             cls_feat = conv(cls_feat)
-        return fam_bbox_pred, refine_anchor, self.odm_cls(cls_feat), self.odm_reg(reg_feat)
+        return self.odm_cls(cls_feat), self.odm_reg(reg_feat)
+
+    @torch.no_grad()
+    def forward_single(self, x, stride):
+        """one level, as the reference's forward_single (s2anet_head.py:207-252)"""
+        fam_bbox_pred, refine_anchor = self._fam(x, stride)
+        cls, reg = self._odm(self.align_conv(x, refine_anchor, stride))
+        return fam_bbox_pred, refine_anchor, cls, reg
+
+    @torch.no_grad()
+    def forward_levels(self, feats):
+        """all levels: FAM per level, then ONE AlignConv call over every level (AlignConv.forward_multi), then ODM per level;
+        level by level the same values as forward_single"""
+        fam = [self._fam(x, s) for x, s in zip(feats, self.anchor_strides)]
+        aligned = self.align_conv.forward_multi(list(feats), [f[1] for f in fam], self.anchor_strides[:len(feats)])
+        return [(f[0], f[1]) + self._odm(a) for f, a in zip(fam, aligned)]
 
     @torch.no_grad()
     def get_bboxes_single(self, cls_score_list, bbox_pred_list, mlvl_anchors, cfg=None, scale_factor=1.0, rescale=True):
@@ -217,7 +261,7 @@ class S2ANetHead(nn.Module):
     def forward(self, feats, img_metas=None, rescale=True):
         """feats: list of (N,C,H_l,W_l) FPN maps -> list over images of (polys (k,8), scores (k,), labels (k,)).
         img_metas (optional): per image a dict with 'scale_factor' (default 1.0), as the reference's get_bboxes reads it."""
-        outs = [self.forward_single(x, s) for x, s in zip(feats, self.anchor_strides)]
+        outs = self.forward_levels(feats)
         num_imgs = feats[0].shape[0]
         results = []
         for i in range(num_imgs):

@@ -1113,3 +1113,47 @@ def test_candidate_queue_full_path(monkeypatch):
     keep1 = ops().nms_rotated.nms_rotated_cuda(d6, order, 0.3, 6)
     assert torch.equal(keep0, keep1)
     assert np.array_equal(bits(iou0.cpu().numpy()), bits(iou1.cpu().numpy()))
+
+
+def test_align_conv_multi_level_equals_per_level():
+    """jdet_align_conv_forward_multi (one persistent tcgen05 launch over all FPN levels) == the per-level calls, bit for bit
+    (same tiles, same K order), and <= 1e-4 from the oracle; level-0 sized map included (cfg4: 8 x 256 x 128 x 128 is checked
+    in test_full_size_cfg4_level0)."""
+    from jdet_b200.models.roi_heads.s2anet_head import AlignConv
+    rng = np.random.default_rng(12)
+    levels = [(40, 8), (20, 16), (10, 32), (5, 64), (3, 128)]
+    m = AlignConv(64, 96, 3).cuda().requires_grad_(False)
+    with torch.no_grad():
+        m.deform_conv.weight.copy_(torch.randn_like(m.deform_conv.weight) * 0.05)
+    xs = [cu(rng.standard_normal((2, 64, hw, hw + 4))) for hw, _ in levels]
+    an = [cu(s2anet_anchors(rng, 2, hw, hw + 4, st)) for hw, st in levels]
+    multi = m.forward_multi(xs, an, [st for _, st in levels])
+    for x, a, (hw, st), o in zip(xs, an, levels, multi):
+        single = m(x, a, st)
+        assert np.array_equal(bits(o.cpu().numpy()), bits(single.cpu().numpy()))
+        want = oracle.align_conv(x.cpu().numpy(), a.cpu().numpy(), st, m.deform_conv.weight.cpu().numpy())
+        assert np.abs(o.cpu().numpy() - want).max() <= TOL
+
+
+def test_full_size_cfg4_level0():
+    """cfg4 level 0 (8 x 256 x 128 x 128) for feature_refine (points 1 and 5: band / stage arithmetic at the bench shape) and
+    AlignConv (1024 tiles on 148 CTAs) against the oracle on sampled positions / a channel slice."""
+    from jdet_b200.models.roi_heads.s2anet_head import AlignConv
+    rng = np.random.default_rng(21)
+    N, C, H, W, st = 8, 256, 128, 128, 8
+    x = torch.randn((N, C, H, W), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    a = s2anet_anchors(rng, N, H, W, st)
+    boxes = cu(a[..., [1, 0, 2, 3, 4]].copy())
+    xn = x.cpu().numpy()
+    for points in (1, 5):
+        got = ops().fr.feature_refine(x, boxes, 1 / st, points)
+        for n, cs in ((0, slice(0, 8)), (7, slice(248, 256)), (3, slice(100, 104))):        # channel slices of three images
+            want = oracle.feature_refine(xn[n:n + 1, cs], a[n:n + 1][..., [1, 0, 2, 3, 4]], 1 / st, points)
+            assert np.abs(got[n:n + 1, cs].cpu().numpy() - want).max() <= TOL
+    m = AlignConv(256, 256, 3).cuda().requires_grad_(False)
+    got = m(x, cu(a), st)
+    w = m.deform_conv.weight.detach().cpu().numpy()
+    for n in (0, 7):                                   # the oracle on a 16-row band of two images (full width, all channels)
+        rows = slice(56, 72)
+        full = oracle.align_conv(xn[n:n + 1], a[n:n + 1], st, w)
+        assert np.abs(got[n:n + 1, :, rows].cpu().numpy() - full[:, :, rows]).max() <= TOL
