@@ -491,7 +491,7 @@ def run_extra(torch, dist, ops, jdist, dev, rank, world, peaks, flush):
     an = [cu(s2anet_anchors(rng, 8, hw, hw, st)) for hw, st in levels]
     bx = [a[..., [1, 0, 2, 3, 4]].contiguous() for a in an]
     for points in (1, 5):
-        fn = lambda: [ops.fr.feature_refine(x, b, 1.0 / st, points) for x, b, (_, st) in zip(xs, bx, levels)]
+        fn = lambda: ops.fr.feature_refine_multi(xs, bx, [1.0 / st for _, st in levels], points)   # the 5 levels in one call
         fn()
         K = 10
         ms = agg(time_steps(torch, fn, K, 3, flush)) / K

@@ -137,6 +137,12 @@ int jdet_roi_align_rotated_backward(int version, const float* grad_output, const
 int jdet_feature_refine(const float* features, const float* best_rbboxes, int N, int C, int H, int W,
                         int points, float spatial_scale, float* output, void* stream);
 
+/* feature_refine on every FPN level of one head in ONE call — FeatureRefineModule.execute (ops/fr.py:331-347) applies FR level by
+ * level; here the levels that qualify for the staged path (points == 1, W % 4 == 0) share one launch.  features / best_rbboxes /
+ * outputs / Hs / Ws / scales: HOST arrays of nlevels (<= 8) entries (device pointers inside); N and C are common.          */
+int jdet_feature_refine_multi(const float* const* features, const float* const* best_rbboxes, int nlevels, int N, int C,
+                              const int* Hs, const int* Ws, const float* scales, int points, float* const* outputs, void* stream);
+
 /* backward w.r.t. features — replaces: FeatureRefineFunction.grad / feature_refine_backward ops/fr.py:242-252,266-271
  * (kernel :167-232).  grad_output (N,C,H,W) -> grad_input (N,C,H,W), fully written. */
 int jdet_feature_refine_backward(const float* grad_output, const float* best_rbboxes, int N, int C, int H, int W,
@@ -182,11 +188,12 @@ int jdet_align_conv_forward(const float* x, const float* anchors, const float* w
 /* the same for every FPN level of one head in ONE call: S2ANetHead applies its AlignConv to 5 levels (s2anet_head.py:230-237);
  * one persistent tcgen05 launch covers all levels' tiles (the 4 / 16 / 64 tiles of the coarse levels fill the last wave
  * instead of costing a launch each) and the weight is split once.  xs / anchors / outs / Hs / Ws / strides: HOST arrays of
- * nlevels (<= 8) entries.  tcgen05 shape class only (else JDET_ERR_UNSUPPORTED: loop over jdet_align_conv_forward).       */
+ * nlevels (<= 8) entries.  x_channels_last != 0: the maps are already (N,H,W,C) in memory (torch.channels_last) and are sampled in
+ * place.  tcgen05 shape class only (else JDET_ERR_UNSUPPORTED: loop over jdet_align_conv_forward).                              */
 size_t jdet_align_conv_forward_multi_workspace_bytes(int nlevels, int N, int C, const int* Hs, const int* Ws, int Co);
 int jdet_align_conv_forward_multi(const float* const* xs, const float* const* anchors, const float* weight, int nlevels,
                                   int N, int C, const int* Hs, const int* Ws, int Co, const float* strides,
-                                  float* const* outs, void* workspace, size_t workspace_bytes, void* stream);
+                                  float* const* outs, int x_channels_last, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

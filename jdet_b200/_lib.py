@@ -43,6 +43,7 @@ SIGNATURES = {
     "jdet_roi_align_rotated_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "jdet_roi_align_rotated_backward": (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _sz, _p]),
     "jdet_feature_refine": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p, _p]),
+    "jdet_feature_refine_multi": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _i, _p, _p]),
     "jdet_feature_refine_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _p, _p]),
     "jdet_align_conv_offset": (_i, [_p, _i, _i, _i, _f, _i, _p, _p]),
     "jdet_deform_conv_forward": (_i, [_p, _p, _p] + [_i] * 16 + [_p, _p]),
@@ -52,7 +53,7 @@ SIGNATURES = {
     "jdet_align_conv_forward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "jdet_align_conv_forward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _sz, _p]),
     "jdet_align_conv_forward_multi_workspace_bytes": (_sz, [_i, _i, _i, _p, _p, _i]),
-    "jdet_align_conv_forward_multi": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _sz, _p]),
+    "jdet_align_conv_forward_multi": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _sz, _p]),
 }
 
 

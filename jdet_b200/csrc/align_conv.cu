@@ -17,7 +17,7 @@ int align_conv_tc_launch(const float* x, const float* anchors, const float* weig
 size_t align_conv_tc_workspace_bytes_multi(int nlevels, int N, int C, const int* Hs, const int* Ws, int Co);
 int align_conv_tc_launch_multi(const float* const* xs, const float* const* anchors, const float* weight, int nlevels, int N, int C,
                                const int* Hs, const int* Ws, int Co, const float* strides, float* const* outs, void* workspace,
-                               cudaStream_t st);
+                               cudaStream_t st, bool x_channels_last);
 }  // namespace jdet
 
 JDET_API const char* jdet_version(void) { return "jdet_b200 0.1.0 sm_100a"; }
@@ -45,7 +45,8 @@ JDET_API int jdet_align_conv_forward(const float* x, const float* anchors, const
 
 // Every FPN level of one head in ONE call (S2ANetHead runs the same AlignConv on its 5 levels, s2anet_head.py:230-237 inside
 // forward_single): one persistent tcgen05 launch over all levels' tiles, one weight split.  xs / anchors / outs / Hs / Ws /
-// strides are HOST arrays of nlevels entries (device pointers inside).  Needs the tcgen05 shape class (C % 16 == 0,
+// strides are HOST arrays of nlevels entries (device pointers inside).  x_channels_last != 0: every xs[l] is already (N,H,W,C) in
+// memory (a torch.channels_last tensor out of the FPN convolutions) and is sampled in place, no re-layout pass.  Needs the tcgen05 shape class (C % 16 == 0,
 // Co % 32 == 0, Co <= 256) and nlevels <= 8, else JDET_ERR_UNSUPPORTED (callers loop over jdet_align_conv_forward).
 JDET_API size_t jdet_align_conv_forward_multi_workspace_bytes(int nlevels, int N, int C, const int* Hs, const int* Ws, int Co) {
   if (nlevels <= 0 || !Hs || !Ws || N <= 0 || C <= 0 || Co <= 0) return 256;
@@ -54,12 +55,14 @@ JDET_API size_t jdet_align_conv_forward_multi_workspace_bytes(int nlevels, int N
 
 JDET_API int jdet_align_conv_forward_multi(const float* const* xs, const float* const* anchors, const float* weight, int nlevels,
                                            int N, int C, const int* Hs, const int* Ws, int Co, const float* strides,
-                                           float* const* outs, void* workspace, size_t workspace_bytes, void* stream) {
+                                           float* const* outs, int x_channels_last, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
   if (nlevels <= 0 || N < 0 || C <= 0 || Co <= 0 || !xs || !anchors || !weight || !Hs || !Ws || !strides || !outs) return JDET_ERR_BAD_ARG;
   if (N == 0) return 0;
   if (nlevels > 8 || !jdet::align_conv_tc_supported(C, Co)) return JDET_ERR_UNSUPPORTED;
   for (int l = 0; l < nlevels; l++)
     if (!xs[l] || !anchors[l] || !outs[l] || Hs[l] <= 0 || Ws[l] <= 0) return JDET_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < jdet_align_conv_forward_multi_workspace_bytes(nlevels, N, C, Hs, Ws, Co)) return JDET_ERR_WORKSPACE;
-  return jdet::align_conv_tc_launch_multi(xs, anchors, weight, nlevels, N, C, Hs, Ws, Co, strides, outs, workspace, (cudaStream_t)stream);
+  return jdet::align_conv_tc_launch_multi(xs, anchors, weight, nlevels, N, C, Hs, Ws, Co, strides, outs, workspace, (cudaStream_t)stream,
+                                          x_channels_last != 0);
 }

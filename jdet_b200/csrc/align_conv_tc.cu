@@ -393,7 +393,7 @@ size_t align_conv_tc_workspace_bytes(int N, int C, int H, int W, int Co) { retur
 // every level of one head in ONE persistent launch (the levels share the weight): re-layout per level, one weight split
 int align_conv_tc_launch_multi(const float* const* xs, const float* const* anchors, const float* weight, int nlevels, int N, int C,
                                const int* Hs, const int* Ws, int Co, const float* strides, float* const* outs, void* workspace,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool x_channels_last) {
   using namespace tc;
   if (nlevels < 1 || nlevels > kMaxLevels) return JDET_ERR_UNSUPPORTED;
   char* wsp = (char*)workspace;
@@ -403,8 +403,12 @@ int align_conv_tc_launch_multi(const float* const* xs, const float* const* ancho
   p.nlevels = nlevels; p.b_hi = b_hi; p.b_lo = b_lo; p.N = N; p.C = C; p.Co = Co;
   long long tiles = 0;
   for (int l = 0; l < nlevels; l++) {
-    float* x_nhwc = (float*)wsp;   wsp += jdet_align_up((size_t)N * C * Hs[l] * Ws[l] * 4, 1024);
-    launch_nchw_to_nhwc(xs[l], x_nhwc, N, C, Hs[l] * Ws[l], st);
+    const float* x_nhwc = xs[l];                    // a map that is already (N,H,W,C) in memory is sampled in place
+    if (!x_channels_last) {
+      float* scratch = (float*)wsp;   wsp += jdet_align_up((size_t)N * C * Hs[l] * Ws[l] * 4, 1024);
+      launch_nchw_to_nhwc(xs[l], scratch, N, C, Hs[l] * Ws[l], st);
+      x_nhwc = scratch;
+    }
     p.lv[l] = Level{x_nhwc, anchors[l], outs[l], Hs[l], Ws[l], strides[l], (int)tiles};
     tiles += ((long long)N * Hs[l] * Ws[l] + kBlockM - 1) / kBlockM;
     if (tiles > 0x7fffffffLL) return JDET_ERR_UNSUPPORTED;
@@ -424,7 +428,7 @@ int align_conv_tc_launch_multi(const float* const* xs, const float* const* ancho
 
 int align_conv_tc_launch(const float* x, const float* anchors, const float* weight, int N, int C, int H, int W, int Co,
                          float stride, float* out, void* workspace, cudaStream_t st) {
-  return align_conv_tc_launch_multi(&x, &anchors, weight, 1, N, C, &H, &W, Co, &stride, &out, workspace, st);
+  return align_conv_tc_launch_multi(&x, &anchors, weight, 1, N, C, &H, &W, Co, &stride, &out, workspace, st, false);
 }
 
 }  // namespace jdet

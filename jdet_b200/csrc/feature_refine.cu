@@ -12,6 +12,7 @@
 // plane (L1 hits).  HBM traffic ~ one read + one write of the feature map: an HBM-bound stream.
 //
 // Layout in HBM: features (N,C,H,W) fp32, boxes (N,H,W,5) fp32, out (N,C,H,W) fp32.
+#include <algorithm>
 #include "common.cuh"
 
 namespace jdet {
@@ -202,15 +203,13 @@ constexpr int kConsumers = kConsumerWarps * 32;
 // pixels (rows 256/W apart): their POINTS tap sets and weights live in registers for the whole channel walk
 // (points = 1: PPT = 4; points = 5: PPT = 2); a sample whose taps leave the staged rows reads them from global.
 template <int POINTS, int PPT>
-__global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_kernel(const float* __restrict__ feat,
-                                                                             const float* __restrict__ boxes, int C, int H,
-                                                                             int W, float spatial_scale, int rows_per_band,
-                                                                             int ch_per_cta, int stages, float* __restrict__ out) {
+__device__ __forceinline__ void fr_tma_body(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
+                                            float spatial_scale, int rows_per_band, int ch_per_cta, int stages,
+                                            float* __restrict__ out, int band, int chunk, int n) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = H * W;
-  const int n = blockIdx.z;
-  const int c0 = blockIdx.y * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
-  const int r0 = blockIdx.x * rows_per_band;                       // first output row of this band
+  const int c0 = chunk * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
+  const int r0 = band * rows_per_band;                             // first output row of this band
   const int lo = max(0, r0 - kHalo), hi = min(H, r0 + rows_per_band + kHalo);   // staged rows [lo, hi)
   const uint32_t band_bytes = (uint32_t)((hi - lo) * W) * 4u;
   const int stage_elems = (rows_per_band + 2 * kHalo) * W;
@@ -300,8 +299,65 @@ __global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_kernel(con
   }
 }
 
+template <int POINTS, int PPT>
+__global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_kernel(const float* __restrict__ feat,
+                                                                             const float* __restrict__ boxes, int C, int H,
+                                                                             int W, float spatial_scale, int rows_per_band,
+                                                                             int ch_per_cta, int stages, float* __restrict__ out) {
+  fr_tma_body<POINTS, PPT>(feat, boxes, C, H, W, spatial_scale, rows_per_band, ch_per_cta, stages, out, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Every FPN level of a head in ONE launch (FeatureRefineModule applies FR to each level, fr.py:339-346): a 1-D grid of
+// (level, image, channel chunk, row band) items, level 0 first.  At cfg4 the five per-level launches took 130 us for 361 MB
+// while level 0 alone streams at 4.3 TB/s; the coarse levels (8 x 8 ... 32 x 32 maps) are launch-bound on their own.
+constexpr int kMaxLevels = 8;
+struct FrLevel { const float* feat; const float* boxes; float* out; int H, W; float scale; int rows, cpc, stages, bands, chunks, item_begin; };
+struct FrLevels { FrLevel lv[kMaxLevels]; int n, C; };
+template <int POINTS, int PPT>
+__global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_multi_kernel(const __grid_constant__ FrLevels L) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxLevels; i++)
+    if (i < L.n && (int)blockIdx.x >= L.lv[i].item_begin) l = i;
+  // a static index per case: the level's scalars stay constant-bank operands (a dynamically indexed parameter struct costs
+  // 24 more registers and the third resident CTA per SM)
+#define JDET_FR_CASE(I)                                                                                                \
+  case I: {                                                                                                            \
+    int item = blockIdx.x - L.lv[I].item_begin;                                                                        \
+    const int band = item % L.lv[I].bands; item /= L.lv[I].bands;                                                      \
+    const int chunk = item % L.lv[I].chunks;                                                                           \
+    fr_tma_body<POINTS, PPT>(L.lv[I].feat, L.lv[I].boxes, L.C, L.lv[I].H, L.lv[I].W, L.lv[I].scale, L.lv[I].rows, L.lv[I].cpc,  \
+                             L.lv[I].stages, L.lv[I].out, band, chunk, item / L.lv[I].chunks);                         \
+    break;                                                                                                             \
+  }
+  switch (l) {
+    JDET_FR_CASE(0) JDET_FR_CASE(1) JDET_FR_CASE(2) JDET_FR_CASE(3) JDET_FR_CASE(4) JDET_FR_CASE(5) JDET_FR_CASE(6) JDET_FR_CASE(7)
+  }
+#undef JDET_FR_CASE
+}
+
 }  // namespace fr_tma
 
+}  // namespace jdet
+
+namespace jdet {
+// band / stage / channel-chunk geometry of the TMA-staged path for one map; false: the map does not qualify.
+static bool fr_tma_config(const float* features, int N, int C, int H, int W, int levels, fr_tma::FrLevel* out) {
+  using namespace fr_tma;
+  const int band_pixels = kConsumers * 4;
+  if (W % 4 != 0 || W > band_pixels || ((uintptr_t)features & 15) != 0) return false;
+  const int rows = max(1, min(H, band_pixels / W));
+  const int stage_elems = (rows + 2 * kHalo) * W;
+  int stages = (int)((64 * 1024) / ((size_t)stage_elems * 4));   // ~64 KB of copies in flight per CTA
+  stages = stages > kMaxStages ? kMaxStages : stages;
+  if (stages < 2) return false;
+  const int bands = jdet_ceil_div(H, rows);
+  int cpc = C;
+  const long long want = 148 * 6;
+  while (cpc > 4 * stages && (long long)bands * jdet_ceil_div(C, cpc) * N < want) cpc = (cpc + 1) / 2;
+  out->H = H; out->W = W; out->rows = rows; out->stages = stages; out->cpc = cpc; out->bands = bands; out->chunks = jdet_ceil_div(C, cpc);
+  return true;
+}
 }  // namespace jdet
 
 // jdet.ops.fr.feature_refine(features, best_rbboxes, spatial_scale, points) (ops/fr.py:255-273)
@@ -319,17 +375,12 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
   // (measured on B200, cfg4: points = 1: 0.130 ms vs 0.203 ms for the 16-B-vector register gather; points = 5 with
   //  PPT = 2 (110 registers, 2 CTAs/SM): 1.14 ms vs 0.68 ms for the register gather — 21 dependent smem reads per
   //  pixel-channel on 16 warps per SM are latency-bound, so points = 5 stays on feature_refine_kernel<5>)
-  const int band_pixels = fr_tma::kConsumers * 4;
-  if (points == 1 && W % 4 == 0 && W <= band_pixels && ((uintptr_t)features & 15) == 0) {
+  fr_tma::FrLevel cfg;
+  if (points == 1 && fr_tma_config(features, N, C, H, W, 1, &cfg)) {
     using namespace fr_tma;
-    const int rows = max(1, min(H, band_pixels / W));
-    const int stage_elems = (rows + 2 * kHalo) * W;
-    int stages = (int)((64 * 1024) / ((size_t)stage_elems * 4));   // ~64 KB of copies in flight per CTA
-    stages = stages > kMaxStages ? kMaxStages : stages;
-    if (stages >= 2) {
-      const int bands = jdet_ceil_div(H, rows);
-      int cpc = C;
-      while (cpc > 4 * stages && (long long)bands * jdet_ceil_div(C, cpc) * N < 148 * 6) cpc = (cpc + 1) / 2;
+    {
+      const int rows = cfg.rows, stages = cfg.stages, cpc = cfg.cpc, bands = cfg.bands;
+      const int stage_elems = (rows + 2 * kHalo) * W;
       const size_t smem = (size_t)stages * stage_elems * 4 + 2 * kMaxStages * sizeof(uint64_t);
       dim3 g(bands, jdet_ceil_div(C, cpc), N);
 #define JDET_LAUNCH_FR_TMA(P, T)                                                                                       \
@@ -358,6 +409,45 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
     feature_refine_p1_vec4_kernel<<<vgrid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, cpc, output);
   } else if (points == 1) feature_refine_kernel<1><<<grid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, output);
   else             feature_refine_kernel<5><<<grid, 256, 0, st>>>(features, best_rbboxes, C, H, W, spatial_scale, ch_per_cta, output);
+  return (int)cudaGetLastError();
+}
+
+// feature_refine on every FPN level of a head in one call (FeatureRefineModule.execute, ops/fr.py:339-346, calls FR per level):
+// the levels that qualify for the TMA-staged path (points == 1, W % 4 == 0) share ONE launch; the others take the per-level
+// kernels.  features / best_rbboxes / outputs / Hs / Ws / scales: HOST arrays of nlevels (<= 8) entries.
+JDET_API int jdet_feature_refine_multi(const float* const* features, const float* const* best_rbboxes, int nlevels, int N, int C,
+                                       const int* Hs, const int* Ws, const float* scales, int points, float* const* outputs,
+                                       void* stream) {
+  using namespace jdet;
+  if (nlevels <= 0 || nlevels > fr_tma::kMaxLevels || N < 0 || C < 0 || !features || !best_rbboxes || !Hs || !Ws || !scales || !outputs ||
+      (points != 1 && points != 5))
+    return JDET_ERR_BAD_ARG;
+  if (N > 65535) return JDET_ERR_UNSUPPORTED;
+  fr_tma::FrLevels L{};
+  L.C = C;
+  long long items = 0;
+  size_t smem = 0;
+  for (int l = 0; l < nlevels; l++) {
+    if (Hs[l] < 0 || Ws[l] < 0) return JDET_ERR_BAD_ARG;
+    if ((size_t)N * C * Hs[l] * Ws[l] == 0) continue;
+    if (!features[l] || !best_rbboxes[l] || !outputs[l]) return JDET_ERR_BAD_ARG;
+    fr_tma::FrLevel v;
+    if (points == 1 && fr_tma_config(features[l], N, C, Hs[l], Ws[l], nlevels, &v)) {
+      v.feat = features[l]; v.boxes = best_rbboxes[l]; v.out = outputs[l]; v.scale = scales[l]; v.item_begin = (int)items;
+      items += (long long)v.bands * v.chunks * N;
+      smem = std::max(smem, (size_t)v.stages * (v.rows + 2 * fr_tma::kHalo) * v.W * 4 + 2 * fr_tma::kMaxStages * sizeof(uint64_t));
+      L.lv[L.n++] = v;
+    } else {
+      const int e = jdet_feature_refine(features[l], best_rbboxes[l], N, C, Hs[l], Ws[l], points, scales[l], outputs[l], stream);
+      if (e) return e;
+    }
+  }
+  if (L.n == 0) return 0;
+  if (items > 0x7fffffffLL) return JDET_ERR_UNSUPPORTED;
+  using namespace fr_tma;
+  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_multi_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_multi_kernel<1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  feature_refine_tma_multi_kernel<1, 4><<<(int)items, kConsumers + 32, smem, (cudaStream_t)stream>>>(L);
   return (int)cudaGetLastError();
 }
 

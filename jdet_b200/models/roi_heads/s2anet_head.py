@@ -99,7 +99,9 @@ class AlignConv(nn.Module):
         if not fused or n > 8 or C % 16 != 0 or Co % 32 != 0 or Co > 256 or xs[0].shape[0] == 0:
             return [self.forward(x, a, s) for x, a, s in zip(xs, anchors_list, strides)]
         require_cuda(*xs, *anchors_list)
-        xx = [f32c(x) for x in xs]
+        # torch.channels_last maps (what cuDNN convolutions produce under that memory format) are sampled in place
+        cl = all(x.dtype == torch.float32 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last) for x in xs)
+        xx = list(xs) if cl else [f32c(x) for x in xs]
         aa = [f32c(a) for a in anchors_list]
         w = f32c(dc.weight.detach())
         N = xx[0].shape[0]
@@ -111,7 +113,7 @@ class AlignConv(nn.Module):
             ws = scratch(L.jdet_align_conv_forward_multi_workspace_bytes(n, N, C, Hs, Ws, Co), xx[0].device)
             check(L.jdet_align_conv_forward_multi(arr([x.data_ptr() for x in xx], ctypes.c_void_p), arr([a.data_ptr() for a in aa], ctypes.c_void_p),
                                                   w.data_ptr(), n, N, C, Hs, Ws, Co, arr([float(s_) for s_ in strides], ctypes.c_float),
-                                                  arr([o.data_ptr() for o in outs], ctypes.c_void_p), ws.data_ptr(), ws.numel(),
+                                                  arr([o.data_ptr() for o in outs], ctypes.c_void_p), int(cl), ws.data_ptr(), ws.numel(),
                                                   stream_ptr(xx[0].device)), "align_conv_multi")
         return outs
 

@@ -57,6 +57,30 @@ def feature_refine(features, best_rbboxes, spatial_scale, points=1):
     return _feature_refine_fwd(features, best_rbboxes, spatial_scale, points)
 
 
+def feature_refine_multi(features_list, best_rbboxes_list, spatial_scales, points=1):
+    """feature_refine on every FPN level in ONE library call (inference; no autograd): the levels share a launch
+    (jdet_feature_refine_multi).  Level by level the same values as feature_refine."""
+    import ctypes
+    assert points in [1, 5]
+    n = len(features_list)
+    require_cuda(*features_list, *best_rbboxes_list)
+    xs = [f32c(x) for x in features_list]
+    bs = [f32c(b) for b in best_rbboxes_list]
+    N, C = xs[0].shape[:2]
+    for x, b in zip(xs, bs):
+        assert x.shape[0] == N and x.shape[1] == C and b.numel() == N * x.shape[2] * x.shape[3] * 5
+    outs = [torch.empty_like(x) for x in xs]
+    if n > 8 or n == 0:
+        return [feature_refine(x, b, s, points) for x, b, s in zip(xs, bs, spatial_scales)]
+    arr = lambda vals, ct: (ct * n)(*vals)
+    with torch.cuda.device(xs[0].device):
+        check(lib().jdet_feature_refine_multi(arr([x.data_ptr() for x in xs], ctypes.c_void_p), arr([b.data_ptr() for b in bs], ctypes.c_void_p),
+                                              n, N, C, arr([x.shape[2] for x in xs], ctypes.c_int), arr([x.shape[3] for x in xs], ctypes.c_int),
+                                              arr([float(s) for s in spatial_scales], ctypes.c_float), points,
+                                              arr([o.data_ptr() for o in outs], ctypes.c_void_p), stream_ptr(xs[0].device)), "feature_refine_multi")
+    return outs
+
+
 class FR(nn.Module):
     def __init__(self, spatial_scale, points=1):
         super().__init__()
@@ -95,10 +119,11 @@ class FeatureRefineModule(nn.Module):
 
     def forward(self, x, best_rbboxes):
         mlvl_rbboxes = [torch.cat(best_rbbox) for best_rbbox in zip(*best_rbboxes)]
-        out = []
-        for x_scale, best_rbboxes_scale, fr_scale in zip(x, mlvl_rbboxes, self.fr):
-            feat_scale = self.conv_5_1(self.conv_1_5(x_scale)) + self.conv_1_1(x_scale)
-            out.append(x_scale + fr_scale(feat_scale, best_rbboxes_scale))
-        return out
+        feats = [self.conv_5_1(self.conv_1_5(x_scale)) + self.conv_1_1(x_scale) for x_scale in x]
+        if not (torch.is_grad_enabled() and any(f.requires_grad for f in feats)) and len({fr.points for fr in self.fr}) == 1:
+            # inference: the per-level FR calls share one launch
+            refined = feature_refine_multi(feats, mlvl_rbboxes, [fr.spatial_scale for fr in self.fr], self.fr[0].points)
+            return [x_scale + r for x_scale, r in zip(x, refined)]
+        return [x_scale + fr_scale(f, b) for x_scale, f, b, fr_scale in zip(x, feats, mlvl_rbboxes, self.fr)]
 
     execute = forward

@@ -1128,6 +1128,9 @@ def test_align_conv_multi_level_equals_per_level():
     xs = [cu(rng.standard_normal((2, 64, hw, hw + 4))) for hw, _ in levels]
     an = [cu(s2anet_anchors(rng, 2, hw, hw + 4, st)) for hw, st in levels]
     multi = m.forward_multi(xs, an, [st for _, st in levels])
+    multi_cl = m.forward_multi([x.contiguous(memory_format=torch.channels_last) for x in xs], an, [st for _, st in levels])
+    for o, o2 in zip(multi, multi_cl):                 # channels_last maps are sampled in place: same bits
+        assert torch.equal(o, o2)
     for x, a, (hw, st), o in zip(xs, an, levels, multi):
         single = m(x, a, st)
         assert np.array_equal(bits(o.cpu().numpy()), bits(single.cpu().numpy()))
@@ -1157,3 +1160,15 @@ def test_full_size_cfg4_level0():
         rows = slice(56, 72)
         full = oracle.align_conv(xn[n:n + 1], a[n:n + 1], st, w)
         assert np.abs(got[n:n + 1, :, rows].cpu().numpy() - full[:, :, rows]).max() <= TOL
+
+
+@pytest.mark.parametrize("points", [1, 5])
+def test_feature_refine_multi_level_equals_per_level(points):
+    """jdet_feature_refine_multi (staged levels share one launch; W % 4 != 0 levels fall back) == per-level feature_refine, bit for bit"""
+    rng = np.random.default_rng(30 + points)
+    shapes = [(40, 48, 8), (20, 24, 16), (10, 12, 32), (5, 6, 64), (3, 3, 128)]       # the last two: W % 4 != 0 -> per-level kernels
+    xs = [cu(rng.standard_normal((2, 48, h, w))) for h, w, _ in shapes]
+    bs = [cu(s2anet_anchors(rng, 2, h, w, st)[..., [1, 0, 2, 3, 4]].copy()) for h, w, st in shapes]
+    multi = ops().fr.feature_refine_multi(xs, bs, [1.0 / st for _, _, st in shapes], points)
+    for x, b, (_, _, st), o in zip(xs, bs, shapes, multi):
+        assert torch.equal(o, ops().fr.feature_refine(x, b, 1.0 / st, points))
