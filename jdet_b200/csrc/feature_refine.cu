@@ -13,6 +13,7 @@
 //
 // Layout in HBM: features (N,C,H,W) fp32, boxes (N,H,W,5) fp32, out (N,C,H,W) fp32.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace jdet {
@@ -22,23 +23,33 @@ struct Tap4 {
   float w1, w2, w3, w4;
 };
 
-// fr.py:18-67
-__device__ __forceinline__ Tap4 fr_tap(float y, float x, int H, int W) {
-  Tap4 t;
-  if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W || !(y == y) || !(x == x)) {
-    t.o00 = -1; t.o01 = t.o10 = t.o11 = 0;          // sample contributes exactly 0 (fr.py:24-26)
-    t.w1 = t.w2 = t.w3 = t.w4 = 0.f;
-    return t;
-  }
+// fr.py:18-67: the sample's cell, its lerp fractions and whether it contributes at all
+struct TapGeo { int yl, xl, yh, xh; float ly, lx; bool valid; };
+__device__ __forceinline__ TapGeo fr_tap_geo(float y, float x, int H, int W) {
+  TapGeo g;
+  g.valid = !(y < -1.0f || y > (float)H || x < -1.0f || x > (float)W || !(y == y) || !(x == x));   // fr.py:24-26: else exactly 0
+  g.yl = g.xl = g.yh = g.xh = 0; g.ly = g.lx = 0.f;
+  if (!g.valid) return g;
   if (y <= 0.f) y = 0.f;
   if (x <= 0.f) x = 0.f;
   int yl = (int)y, xl = (int)x, yh, xh;
   if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
   if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
-  const float ly = y - (float)yl, lx = x - (float)xl;
-  const float hy = 1.f - ly, hx = 1.f - lx;
-  t.o00 = yl * W + xl; t.o01 = yl * W + xh; t.o10 = yh * W + xl; t.o11 = yh * W + xh;
-  t.w1 = __fmul_rn(hy, hx); t.w2 = __fmul_rn(hy, lx); t.w3 = __fmul_rn(ly, hx); t.w4 = __fmul_rn(ly, lx);
+  g.yl = yl; g.xl = xl; g.yh = yh; g.xh = xh;
+  g.ly = y - (float)yl; g.lx = x - (float)xl;
+  return g;
+}
+__device__ __forceinline__ Tap4 fr_tap(float y, float x, int H, int W) {
+  Tap4 t;
+  const TapGeo g = fr_tap_geo(y, x, H, W);
+  if (!g.valid) {
+    t.o00 = -1; t.o01 = t.o10 = t.o11 = 0;          // sample contributes exactly 0 (fr.py:24-26)
+    t.w1 = t.w2 = t.w3 = t.w4 = 0.f;
+    return t;
+  }
+  const float hy = 1.f - g.ly, hx = 1.f - g.lx;
+  t.o00 = g.yl * W + g.xl; t.o01 = g.yl * W + g.xh; t.o10 = g.yh * W + g.xl; t.o11 = g.yh * W + g.xh;
+  t.w1 = __fmul_rn(hy, hx); t.w2 = __fmul_rn(hy, g.lx); t.w3 = __fmul_rn(g.ly, hx); t.w4 = __fmul_rn(g.ly, g.lx);
   return t;
 }
 
@@ -173,69 +184,136 @@ __global__ void __launch_bounds__(256, 2) feature_refine_bwd_kernel(const float*
 // CTA = (row band, channel slab, image), one thread per pixel of the band.
 // the 1 or 5 sample points of a box (fr.py:128-153), decoded into taps
 template <int POINTS>
-__device__ __forceinline__ void fr_decode(const float* __restrict__ bb, float spatial_scale, int H, int W, Tap4 (&taps)[POINTS]) {
+__device__ __forceinline__ void fr_points(const float* __restrict__ bb, float spatial_scale, float (&py)[POINTS], float (&px)[POINTS]) {
   const float roi_y = __fmul_rn(__ldg(bb), spatial_scale), roi_x = __fmul_rn(__ldg(bb + 1), spatial_scale);
-  taps[0] = fr_tap(roi_y, roi_x, H, W);
-  if (POINTS > 1) {
+  py[0] = roi_y; px[0] = roi_x;
+  if (POINTS > 1) {   // fr.py:139-153
     const float rw = __fmul_rn(__ldg(bb + 2), spatial_scale), rh = __fmul_rn(__ldg(bb + 3), spatial_scale), ra = __ldg(bb + 4);
     const float w2 = rw * 0.5f, h2 = rh * 0.5f;
     const float ca = cosf(ra), sa = sinf(ra);
     const float wx = __fmul_rn(ca, w2), wy = __fmul_rn(sa, w2), hx = __fmul_rn(-sa, h2), hy = __fmul_rn(ca, h2);
-    taps[1 % POINTS] = fr_tap(__fadd_rn(__fadd_rn(roi_y, wy), hy), __fadd_rn(__fadd_rn(roi_x, wx), hx), H, W);
-    taps[2 % POINTS] = fr_tap(__fadd_rn(__fsub_rn(roi_y, wy), hy), __fadd_rn(__fsub_rn(roi_x, wx), hx), H, W);
-    taps[3 % POINTS] = fr_tap(__fsub_rn(__fsub_rn(roi_y, wy), hy), __fsub_rn(__fsub_rn(roi_x, wx), hx), H, W);
-    taps[4 % POINTS] = fr_tap(__fsub_rn(__fadd_rn(roi_y, wy), hy), __fsub_rn(__fadd_rn(roi_x, wx), hx), H, W);
+    py[1 % POINTS] = __fadd_rn(__fadd_rn(roi_y, wy), hy); px[1 % POINTS] = __fadd_rn(__fadd_rn(roi_x, wx), hx);
+    py[2 % POINTS] = __fadd_rn(__fsub_rn(roi_y, wy), hy); px[2 % POINTS] = __fadd_rn(__fsub_rn(roi_x, wx), hx);
+    py[3 % POINTS] = __fsub_rn(__fsub_rn(roi_y, wy), hy); px[3 % POINTS] = __fsub_rn(__fsub_rn(roi_x, wx), hx);
+    py[4 % POINTS] = __fsub_rn(__fadd_rn(roi_y, wy), hy); px[4 % POINTS] = __fsub_rn(__fadd_rn(roi_x, wx), hx);
   }
+}
+template <int POINTS>
+__device__ __forceinline__ void fr_decode(const float* __restrict__ bb, float spatial_scale, int H, int W, Tap4 (&taps)[POINTS]) {
+  float py[POINTS], px[POINTS];
+  fr_points<POINTS>(bb, spatial_scale, py, px);
+#pragma unroll
+  for (int k = 0; k < POINTS; k++) taps[k] = fr_tap(py[k], px[k], H, W);
 }
 
 namespace fr_tma {
 
-constexpr int kHalo = 4;
 constexpr int kMaxStages = 8;
 
-constexpr int kConsumerWarps = 8;
-constexpr int kConsumers = kConsumerWarps * 32;
+// the geometry of one instantiation: CW consumer warps, PPT pixels per consumer thread, HALO staged rows either side of the band
+template <int POINTS> struct Geo;
+template <> struct Geo<1> { static constexpr int CW = 8, PPT = 4, HALO = 4, MINB = 3; };   // 3 CTAs per SM: 72 registers
+// points = 5: HALO bounds the stage (rows_per_band + 2 * HALO rows); the rows actually staged are those the band's samples read
+// (fr_tma_body<5>: 21 of the 32-row capacity on average at cfg4's 128 x 128 level, whose 4-cell anchors' corners reach +-9 rows)
+#ifndef JDET_FR5_CW          // A/B switches (tools/ab_libs.py build NAME=flags:-DJDET_FR5_CW=8 -DJDET_FR5_PPT=4 ...)
+#define JDET_FR5_CW 16
+#endif
+#ifndef JDET_FR5_PPT
+#define JDET_FR5_PPT 2
+#endif
+#ifndef JDET_FR5_HALO
+#define JDET_FR5_HALO 12
+#endif
+#ifndef JDET_FR5_SMEM_KB
+#define JDET_FR5_SMEM_KB 104
+#endif
+#ifndef JDET_FR5_MINB
+#define JDET_FR5_MINB 1
+#endif
+template <> struct Geo<5> { static constexpr int CW = JDET_FR5_CW, PPT = JDET_FR5_PPT, HALO = JDET_FR5_HALO, MINB = JDET_FR5_MINB; };
+// floats per stage: the band, then (points = 5) a zero pad of one row + 8 words that no copy ever writes: a sample outside the
+// map reads its 2 x 2 taps there (see fr_tma_body<5>)
+template <int POINTS>
+__host__ __device__ constexpr int fr_zero_pad(int W) { return POINTS == 5 ? W + 8 : 0; }
+template <int POINTS>
+__host__ __device__ constexpr int fr_stage_elems(int rows_per_band, int W) {
+  return (rows_per_band + 2 * Geo<POINTS>::HALO) * W + fr_zero_pad<POINTS>(W);
+}
 
-// CTA = 8 consumer warps + 1 producer warp; grid = (row bands, channel chunks, N).  A band is 256*PPT / W
-// full-width rows (+ kHalo rows either side): contiguous in an NCHW plane, so one cp.async.bulk per channel
+// CTA = CW consumer warps + 1 producer warp; grid = (row bands, channel chunks, N).  A band is CW*32*PPT / W
+// full-width rows (+ HALO rows either side): contiguous in an NCHW plane, so one cp.async.bulk per channel
 // stages it.  The producer lane only waits on empty[] and issues copies; the consumers never block on a
-// refill, and `stages` channels per CTA x several CTAs per SM are in flight.  Each consumer thread owns PPT
-// pixels (rows 256/W apart): their POINTS tap sets and weights live in registers for the whole channel walk
-// (points = 1: PPT = 4; points = 5: PPT = 2); a sample whose taps leave the staged rows reads them from global.
-template <int POINTS, int PPT>
+// refill, and `stages` channels per CTA x the CTAs of the SM are in flight.  Each consumer thread owns PPT
+// pixels (rows CW*32/W apart): their POINTS tap sets and weights live in registers for the whole channel walk;
+// a sample whose taps leave the staged rows reads them from global.
+//
+// points = 5 (21 shared-memory reads per pixel-channel): a thread whose samples are all staged (or outside the map: those point
+// at the stage's zero word with zero weights, contributing the reference's exact 0) runs a branch-free body, so its 42 reads
+// are issued back to back; per-sample branches (each a read -> FMA round trip) made the first version of this path
+// latency-bound at 1.14 ms where the L1 gather took 0.68 ms.
+// shared-memory ring of one CTA: `stages` bands of stage_elems floats, then the full[] / empty[] barriers and two words
+// (points = 5: the first / last row the band's samples touch)
+template <int POINTS>
+struct FrRing {
+  float* ring; uint64_t* full; uint64_t* empty; int* span;
+  int lo, hi, zoff, stage_elems;                                                 // staged rows [lo, hi)
+  __device__ __forceinline__ FrRing(unsigned char* smem, int H, int W, int r0, int rows_per_band, int stages) {
+    constexpr int kHalo = Geo<POINTS>::HALO;
+    lo = max(0, r0 - kHalo); hi = min(H, r0 + rows_per_band + kHalo);
+    zoff = (rows_per_band + 2 * kHalo) * W;                                      // the stage's zero pad
+    stage_elems = fr_stage_elems<POINTS>(rows_per_band, W);
+    ring = reinterpret_cast<float*>(smem);
+    full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * stage_elems);
+    empty = full + kMaxStages;
+    span = reinterpret_cast<int*>(empty + kMaxStages);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+      for (int s = 0; s < stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], Geo<POINTS>::CW); }
+      mbar_init_fence();
+      span[0] = 0x7fffffff; span[1] = -1;
+    }
+    const int pad = fr_zero_pad<POINTS>(W);                                      // no copy ever writes it
+    for (int i = tid; i < stages * pad; i += blockDim.x) ring[(size_t)(i / pad) * stage_elems + zoff + i % pad] = 0.f;
+    __syncthreads();
+  }
+  // the producer lane: one bulk copy per channel, `stages` in flight
+  __device__ __forceinline__ void produce(const float* plane0, int HW, int W, int nch, int stages) const {
+    const uint32_t band_bytes = (uint32_t)((hi - lo) * W) * 4u;
+    const float* src0 = plane0 + (size_t)lo * W;
+    uint32_t stage = 0, phase = 0;
+    for (int c = 0; c < nch; c++) {
+      if (c >= stages) mbar_wait(&empty[stage], phase ^ 1);        // consumers released the previous occupant
+      mbar_expect_tx(&full[stage], band_bytes);
+      bulk_g2s(ring + (size_t)stage * stage_elems, src0 + (size_t)c * HW, band_bytes, &full[stage]);
+      if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
+    }
+  }
+};
+constexpr size_t kRingTail = 2 * kMaxStages * sizeof(uint64_t) + 16;             // barriers + span
+
+template <int POINTS>
 __device__ __forceinline__ void fr_tma_body(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
                                             float spatial_scale, int rows_per_band, int ch_per_cta, int stages,
-                                            float* __restrict__ out, int band, int chunk, int n) {
+                                            float* __restrict__ out, int band, int chunk, int n);
+
+// points = 1
+template <>
+__device__ __forceinline__ void fr_tma_body<1>(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
+                                               float spatial_scale, int rows_per_band, int ch_per_cta, int stages,
+                                               float* __restrict__ out, int band, int chunk, int n) {
+  constexpr int POINTS = 1, PPT = Geo<1>::PPT, kConsumers = Geo<1>::CW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = H * W;
   const int c0 = chunk * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
   const int r0 = band * rows_per_band;                             // first output row of this band
-  const int lo = max(0, r0 - kHalo), hi = min(H, r0 + rows_per_band + kHalo);   // staged rows [lo, hi)
-  const uint32_t band_bytes = (uint32_t)((hi - lo) * W) * 4u;
-  const int stage_elems = (rows_per_band + 2 * kHalo) * W;
-  float* ring = reinterpret_cast<float*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * stage_elems);
-  uint64_t* empty = full + kMaxStages;
+  const FrRing<1> R(smem_raw, H, W, r0, rows_per_band, stages);
+  const int lo = R.lo, hi = R.hi, stage_elems = R.stage_elems;
+  const float* ring = R.ring;
   const int tid = threadIdx.x, lane = tid & 31;
   const int nch = c1 - c0;
 
-  if (tid == 0) {
-    for (int s = 0; s < stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
-    mbar_init_fence();
-  }
-  __syncthreads();
-
   if (tid >= kConsumers) {                                         // ---- producer warp
-    if (lane == 0) {
-      const float* src0 = feat + ((size_t)n * C + c0) * HW + (size_t)lo * W;
-      uint32_t stage = 0, phase = 0;
-      for (int c = 0; c < nch; c++) {
-        if (c >= stages) mbar_wait(&empty[stage], phase ^ 1);      // consumers released the previous occupant
-        mbar_expect_tx(&full[stage], band_bytes);
-        bulk_g2s(ring + (size_t)stage * stage_elems, src0 + (size_t)c * HW, band_bytes, &full[stage]);
-        if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
-      }
-    }
+    if (lane == 0) R.produce(feat + ((size_t)n * C + c0) * HW, HW, W, nch, stages);
     return;
   }
 
@@ -271,7 +349,7 @@ __device__ __forceinline__ void fr_tma_body(const float* __restrict__ feat, cons
 
   uint32_t stage = 0, phase = 0;
   for (int c = 0; c < nch; c++) {
-    mbar_wait(&full[stage], phase);
+    mbar_wait(&R.full[stage], phase);
     const float* sp = ring + (size_t)stage * stage_elems;
     float v[PPT];
 #pragma unroll
@@ -292,19 +370,160 @@ __device__ __forceinline__ void fr_tma_body(const float* __restrict__ feat, cons
     for (int j = 0; j < PPT; j++)
       if (pc[j] >= 0) st_stream(dst + pc[j], v[j]);
     __syncwarp();                                                  // every lane issued its stores, so its smem reads returned
-    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (lane == 0) mbar_arrive(&R.empty[stage]);
     dst += HW;
     gplane += HW;
     if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
   }
 }
 
-template <int POINTS, int PPT>
-__global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_kernel(const float* __restrict__ feat,
-                                                                             const float* __restrict__ boxes, int C, int H,
-                                                                             int W, float spatial_scale, int rows_per_band,
-                                                                             int ch_per_cta, int stages, float* __restrict__ out) {
-  fr_tma_body<POINTS, PPT>(feat, boxes, C, H, W, spatial_scale, rows_per_band, ch_per_cta, stages, out, blockIdx.x, blockIdx.y, blockIdx.z);
+// points = 5: 21 shared-memory reads per pixel-channel.  What bounds it is shared-memory wavefronts (the corners of independent
+// boxes land in arbitrary banks: ~2.5 wavefronts per read), so issue slots are plentiful and registers are what is scarce: a sample
+// is kept as ONE word (byte offset of its top-left tap inside the stage) plus its two
+// lerp fractions, and the four weights are re-formed per channel exactly as fr.py:57-63 forms them — 15 registers per pixel
+// instead of 40, which leaves the compiler room to issue a pixel's 21 reads back to back (with the taps in 80 registers and a
+// per-sample staged-or-global branch the first version of this path serialised read -> FMA -> read and ran at 1.14 ms where the
+// L1 gather takes 0.68 ms).  A sample outside the map points at the stage's zero pad (contributes the reference's exact 0;
+// finite features assumed: a non-finite value in the column / row next to a clamped tap would turn its 0 weight into NaN).
+// A thread with a sample outside the staged rows (0.02 % at cfg4) walks its pixels' taps from a local-memory table, all from global.
+template <>
+__device__ __forceinline__ void fr_tma_body<5>(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
+                                               float spatial_scale, int rows_per_band, int ch_per_cta, int stages,
+                                               float* __restrict__ out, int band, int chunk, int n) {
+  constexpr int POINTS = 5, PPT = Geo<5>::PPT, kConsumers = Geo<5>::CW * 32, kHalo = Geo<5>::HALO;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int HW = H * W;
+  const int c0 = chunk * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
+  const int r0 = band * rows_per_band, r1 = min(H, r0 + rows_per_band);
+  FrRing<5> R(smem_raw, H, W, r0, rows_per_band, stages);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nch = c1 - c0;
+  const int band_px = (r1 - r0) * W;
+
+  // ---- every sample of the band: its cell and fractions; the rows the band touches
+  uint32_t ta[PPT][POINTS];                                        // top-left tap: map offset, then byte offset in the stage
+  float tly[PPT][POINTS], tlx[PPT][POINTS];
+  int tmin = 0x7fffffff, tmax = -1;                                // first / last row this thread's samples read
+  bool global_only = false;                                        // a sample that cannot be staged at all
+  if (tid < kConsumers) {
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+      const int i = tid + j * kConsumers;
+#pragma unroll
+      for (int k = 0; k < POINTS; k++) { ta[j][k] = 0xffffffffu; tly[j][k] = 0.f; tlx[j][k] = 0.f; }
+      if (i < band_px) {
+        float py[POINTS], px[POINTS];
+        fr_points<POINTS>(boxes + ((size_t)n * HW + r0 * W + i) * 5, spatial_scale, py, px);
+#pragma unroll
+        for (int k = 0; k < POINTS; k++) {
+          TapGeo g = fr_tap_geo(py[k], px[k], H, W);
+          if (!g.valid) continue;
+          // where the reference clamps the lower / right neighbour onto the tap itself (last row / column, fr.py:40-52: fraction
+          // exactly 0) the 2 x 2 cell is moved one row / column back with fraction exactly 1: the same two products in the same
+          // order, and every read stays inside the map.  (H == 1 cannot: that sample reads global memory.)
+          if (g.yh == g.yl) { if (H < 2) { global_only = true; continue; } g.yl -= 1; g.ly = 1.f; }
+          if (g.xh == g.xl) { g.xl -= 1; g.lx = 1.f; }             // W % 4 == 0: W >= 4
+          ta[j][k] = (uint32_t)(g.yl * W + g.xl);
+          tly[j][k] = g.ly; tlx[j][k] = g.lx;
+          tmin = min(tmin, g.yl); tmax = max(tmax, g.yl + 1);
+        }
+      }
+    }
+    int wmin = tmin, wmax = tmax;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, o)); wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o)); }
+    if (lane == 0) { atomicMin(&R.span[0], max(wmin, 0)); atomicMax(&R.span[1], wmax); }
+  }
+  __syncthreads();
+  {
+    // the staged window: every row the band's samples read when that fits the stage (rows_per_band + 2 * kHalo rows), else the
+    // band and kHalo rows either side (the samples beyond read global memory)
+    const int need_lo = min(r0, R.span[0]), need_hi = max(r1, R.span[1] + 1);
+    if (need_hi - need_lo <= rows_per_band + 2 * kHalo) { R.lo = need_lo; R.hi = need_hi; }
+  }
+  const int lo = R.lo, hi = R.hi;
+
+  if (tid >= kConsumers) {
+    if (lane == 0) R.produce(feat + ((size_t)n * C + c0) * HW, HW, W, nch, stages);
+    return;
+  }
+
+  const bool straight = !global_only && (tmax < 0 || (tmin >= lo && tmax < hi));   // every sample of this thread reads shared memory
+  Tap4 gt[PPT][POINTS];                                            // global taps, only touched when !straight (local memory)
+  const uint32_t zb = (uint32_t)R.zoff * 4u, wb = (uint32_t)W * 4u;
+#pragma unroll
+  for (int j = 0; j < PPT; j++)
+#pragma unroll
+    for (int k = 0; k < POINTS; k++) ta[j][k] = ta[j][k] == 0xffffffffu ? zb : (ta[j][k] - (uint32_t)(lo * W)) * 4u;
+  if (!straight) {
+#pragma unroll 1
+    for (int j = 0; j < PPT; j++) {
+      const int i = tid + j * kConsumers;
+      if (i < band_px) fr_decode<POINTS>(boxes + ((size_t)n * HW + r0 * W + i) * 5, spatial_scale, H, W, gt[j]);
+    }
+  }
+  const size_t plane0 = ((size_t)n * C + c0) * HW;
+  float* dst = out + plane0 + (size_t)r0 * W + tid;                // pixel j of this thread: dst[j * kConsumers]
+  const float* gplane = feat + plane0;
+  const uint32_t cb = (uint32_t)((r0 - lo) * W + tid) * 4u;        // centre of pixel 0, byte offset in the stage
+  const unsigned char* ring_b = reinterpret_cast<const unsigned char*>(R.ring);
+  const uint32_t stage_bytes = (uint32_t)R.stage_elems * 4u;
+  const unsigned char* sb = ring_b;
+
+  uint32_t stage = 0, phase = 0;
+  for (int c = 0; c < nch; c++) {
+    mbar_wait(&R.full[stage], phase);
+    auto at = [&](uint32_t off) { return *reinterpret_cast<const float*>(sb + off); };
+    if (straight) {
+      float v[PPT];
+#pragma unroll
+      for (int j = 0; j < PPT; j++) {
+        const bool exists = tid + j * kConsumers < band_px;
+        v[j] = at(exists ? cb + (uint32_t)(j * kConsumers) * 4u : zb);
+#pragma unroll
+        for (int k = 0; k < POINTS; k++) {
+          uint32_t a = ta[j][k];
+          float ly = tly[j][k], lx = tlx[j][k];
+          // opaque to the optimiser: without this the weights and the four offsets are hoisted out of the channel loop and
+          // the 15 registers per pixel are 40 again
+          asm volatile("" : "+r"(a), "+f"(ly), "+f"(lx));
+          const float hy = 1.f - ly, hx = 1.f - lx;
+          const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
+          v[j] += w1 * at(a) + w2 * at(a + 4u) + w3 * at(a + wb) + w4 * at(a + wb + 4u);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PPT; j++)
+        if (tid + j * kConsumers < band_px) st_stream(dst + j * kConsumers, v[j]);
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < PPT; j++) {
+        if (tid + j * kConsumers >= band_px) break;
+        float v = at(cb + (uint32_t)(j * kConsumers) * 4u);
+#pragma unroll
+        for (int k = 0; k < POINTS; k++) {
+          const Tap4 t = gt[j][k];
+          if (t.o00 >= 0)
+            v += t.w1 * __ldg(gplane + t.o00) + t.w2 * __ldg(gplane + t.o01) + t.w3 * __ldg(gplane + t.o10) + t.w4 * __ldg(gplane + t.o11);
+        }
+        st_stream(dst + j * kConsumers, v);
+      }
+    }
+    __syncwarp();                                                  // every lane issued its stores, so its smem reads returned
+    if (lane == 0) mbar_arrive(&R.empty[stage]);
+    dst += HW;
+    gplane += HW;
+    sb += stage_bytes;
+    if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; sb = ring_b; }
+  }
+}
+
+template <int POINTS>
+__global__ void __launch_bounds__(Geo<POINTS>::CW * 32 + 32, Geo<POINTS>::MINB) feature_refine_tma_kernel(const float* __restrict__ feat,
+                                                                                       const float* __restrict__ boxes, int C, int H,
+                                                                                       int W, float spatial_scale, int rows_per_band,
+                                                                                       int ch_per_cta, int stages, float* __restrict__ out) {
+  fr_tma_body<POINTS>(feat, boxes, C, H, W, spatial_scale, rows_per_band, ch_per_cta, stages, out, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // Every FPN level of a head in ONE launch (FeatureRefineModule applies FR to each level, fr.py:339-346): a 1-D grid of
@@ -313,8 +532,8 @@ __global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_kernel(con
 constexpr int kMaxLevels = 8;
 struct FrLevel { const float* feat; const float* boxes; float* out; int H, W; float scale; int rows, cpc, stages, bands, chunks, item_begin; };
 struct FrLevels { FrLevel lv[kMaxLevels]; int n, C; };
-template <int POINTS, int PPT>
-__global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_multi_kernel(const __grid_constant__ FrLevels L) {
+template <int POINTS>
+__global__ void __launch_bounds__(Geo<POINTS>::CW * 32 + 32, Geo<POINTS>::MINB) feature_refine_tma_multi_kernel(const __grid_constant__ FrLevels L) {
   int l = 0;
 #pragma unroll
   for (int i = 1; i < kMaxLevels; i++)
@@ -326,8 +545,8 @@ __global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_multi_kern
     int item = blockIdx.x - L.lv[I].item_begin;                                                                        \
     const int band = item % L.lv[I].bands; item /= L.lv[I].bands;                                                      \
     const int chunk = item % L.lv[I].chunks;                                                                           \
-    fr_tma_body<POINTS, PPT>(L.lv[I].feat, L.lv[I].boxes, L.C, L.lv[I].H, L.lv[I].W, L.lv[I].scale, L.lv[I].rows, L.lv[I].cpc,  \
-                             L.lv[I].stages, L.lv[I].out, band, chunk, item / L.lv[I].chunks);                         \
+    fr_tma_body<POINTS>(L.lv[I].feat, L.lv[I].boxes, L.C, L.lv[I].H, L.lv[I].W, L.lv[I].scale, L.lv[I].rows, L.lv[I].cpc,       \
+                        L.lv[I].stages, L.lv[I].out, band, chunk, item / L.lv[I].chunks);                              \
     break;                                                                                                             \
   }
   switch (l) {
@@ -340,15 +559,21 @@ __global__ void __launch_bounds__(kConsumers + 32) feature_refine_tma_multi_kern
 
 }  // namespace jdet
 
+JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxes, int N, int C, int H, int W,
+                                 int points, float spatial_scale, float* output, void* stream);
+
 namespace jdet {
 // band / stage / channel-chunk geometry of the TMA-staged path for one map; false: the map does not qualify.
-static bool fr_tma_config(const float* features, int N, int C, int H, int W, int levels, fr_tma::FrLevel* out) {
+template <int POINTS>
+static bool fr_tma_config(const float* features, int N, int C, int H, int W, fr_tma::FrLevel* out) {
   using namespace fr_tma;
-  const int band_pixels = kConsumers * 4;
+  using G = Geo<POINTS>;
+  const int band_pixels = G::CW * 32 * G::PPT;
   if (W % 4 != 0 || W > band_pixels || ((uintptr_t)features & 15) != 0) return false;
   const int rows = max(1, min(H, band_pixels / W));
-  const int stage_elems = (rows + 2 * kHalo) * W;
-  int stages = (int)((64 * 1024) / ((size_t)stage_elems * 4));   // ~64 KB of copies in flight per CTA
+  const size_t stage_bytes = (size_t)fr_stage_elems<POINTS>(rows, W) * 4;
+  // points = 1: ~64 KB of copies in flight per CTA, 3 CTAs per SM; points = 5: one 17-warp CTA per SM, ~100 KB
+  int stages = (int)((POINTS == 1 ? 64 * 1024 : JDET_FR5_SMEM_KB * 1024) / stage_bytes);
   stages = stages > kMaxStages ? kMaxStages : stages;
   if (stages < 2) return false;
   const int bands = jdet_ceil_div(H, rows);
@@ -357,6 +582,59 @@ static bool fr_tma_config(const float* features, int N, int C, int H, int W, int
   while (cpc > 4 * stages && (long long)bands * jdet_ceil_div(C, cpc) * N < want) cpc = (cpc + 1) / 2;
   out->H = H; out->W = W; out->rows = rows; out->stages = stages; out->cpc = cpc; out->bands = bands; out->chunks = jdet_ceil_div(C, cpc);
   return true;
+}
+template <int POINTS>
+static size_t fr_tma_smem(const fr_tma::FrLevel& v) {
+  using namespace fr_tma;
+  return (size_t)v.stages * fr_stage_elems<POINTS>(v.rows, v.W) * 4 + kRingTail;
+}
+
+template <int POINTS>
+static int fr_tma_launch(const float* features, const float* best_rbboxes, int N, int C, int H, int W, float spatial_scale,
+                         float* output, cudaStream_t st, bool* taken) {
+  using namespace fr_tma;
+  FrLevel cfg;
+  *taken = fr_tma_config<POINTS>(features, N, C, H, W, &cfg);
+  if (!*taken) return 0;
+  const size_t smem = fr_tma_smem<POINTS>(cfg);
+  dim3 g(cfg.bands, cfg.chunks, N);
+  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<POINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // without this the driver picks the smallest carve-out that fits ONE block (ncu: occupancy_limit_shared_mem = 1)
+  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<POINTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  feature_refine_tma_kernel<POINTS><<<g, Geo<POINTS>::CW * 32 + 32, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, cfg.rows, cfg.cpc,
+                                                                                cfg.stages, output);
+  return (int)cudaGetLastError();
+}
+
+template <int POINTS>
+static int fr_multi(const float* const* features, const float* const* best_rbboxes, int nlevels, int N, int C, const int* Hs, const int* Ws,
+                    const float* scales, float* const* outputs, void* stream) {
+  using namespace fr_tma;
+  FrLevels L{};
+  L.C = C;
+  long long items = 0;
+  size_t smem = 0;
+  for (int l = 0; l < nlevels; l++) {
+    if (Hs[l] < 0 || Ws[l] < 0) return JDET_ERR_BAD_ARG;
+    if ((size_t)N * C * Hs[l] * Ws[l] == 0) continue;
+    if (!features[l] || !best_rbboxes[l] || !outputs[l]) return JDET_ERR_BAD_ARG;
+    FrLevel v;
+    if (fr_tma_config<POINTS>(features[l], N, C, Hs[l], Ws[l], &v)) {
+      v.feat = features[l]; v.boxes = best_rbboxes[l]; v.out = outputs[l]; v.scale = scales[l]; v.item_begin = (int)items;
+      items += (long long)v.bands * v.chunks * N;
+      smem = std::max(smem, fr_tma_smem<POINTS>(v));
+      L.lv[L.n++] = v;
+    } else {
+      const int e = jdet_feature_refine(features[l], best_rbboxes[l], N, C, Hs[l], Ws[l], POINTS, scales[l], outputs[l], stream);
+      if (e) return e;
+    }
+  }
+  if (L.n == 0) return 0;
+  if (items > 0x7fffffffLL) return JDET_ERR_UNSUPPORTED;
+  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_multi_kernel<POINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_multi_kernel<POINTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  feature_refine_tma_multi_kernel<POINTS><<<(int)items, Geo<POINTS>::CW * 32 + 32, smem, (cudaStream_t)stream>>>(L);
+  return (int)cudaGetLastError();
 }
 }  // namespace jdet
 
@@ -370,31 +648,13 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
   if (N > 65535) return JDET_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W;
-  // TMA-staged path: full-width row bands (contiguous in NCHW), one thread per pixel of the band
-  // TMA-staged path: full-width row bands (contiguous in NCHW)
-  // (measured on B200, cfg4: points = 1: 0.130 ms vs 0.203 ms for the 16-B-vector register gather; points = 5 with
-  //  PPT = 2 (110 registers, 2 CTAs/SM): 1.14 ms vs 0.68 ms for the register gather — 21 dependent smem reads per
-  //  pixel-channel on 16 warps per SM are latency-bound, so points = 5 stays on feature_refine_kernel<5>)
-  fr_tma::FrLevel cfg;
-  if (points == 1 && fr_tma_config(features, N, C, H, W, 1, &cfg)) {
-    using namespace fr_tma;
-    {
-      const int rows = cfg.rows, stages = cfg.stages, cpc = cfg.cpc, bands = cfg.bands;
-      const int stage_elems = (rows + 2 * kHalo) * W;
-      const size_t smem = (size_t)stages * stage_elems * 4 + 2 * kMaxStages * sizeof(uint64_t);
-      dim3 g(bands, jdet_ceil_div(C, cpc), N);
-#define JDET_LAUNCH_FR_TMA(P, T)                                                                                       \
-  do {                                                                                                                 \
-    JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    /* without this the driver picks the smallest carve-out that fits ONE block (ncu: occupancy_limit_shared_mem = 1) */ \
-    JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_kernel<P, T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
-    feature_refine_tma_kernel<P, T><<<g, kConsumers + 32, smem, st>>>(features, best_rbboxes, C, H, W, spatial_scale, rows, cpc, stages, output); \
-  } while (0)
-      JDET_LAUNCH_FR_TMA(1, 4);
-#undef JDET_LAUNCH_FR_TMA
-      return (int)cudaGetLastError();
-    }
-  }
+  // TMA-staged path: full-width row bands (contiguous in NCHW), PPT pixels of the band per thread
+  // (measured on B200, cfg4: points = 1: 0.130 ms vs 0.203 ms for the 16-B-vector register gather)
+  static const bool no_staged_p5 = getenv("JDET_FR_P5_GATHER") != nullptr;      // A/B: points = 5 on the L1 gather kernel
+  bool taken = false;
+  const int e = points == 1 ? fr_tma_launch<1>(features, best_rbboxes, N, C, H, W, spatial_scale, output, st, &taken)
+                : no_staged_p5 ? 0 : fr_tma_launch<5>(features, best_rbboxes, N, C, H, W, spatial_scale, output, st, &taken);
+  if (e || taken) return e;
   const int ptiles = jdet_ceil_div(HW, 256);
   // enough CTAs to fill 148 SMs several times over, but keep slabs long enough to amortise the box decode
   int ch_per_cta = C;
@@ -413,7 +673,7 @@ JDET_API int jdet_feature_refine(const float* features, const float* best_rbboxe
 }
 
 // feature_refine on every FPN level of a head in one call (FeatureRefineModule.execute, ops/fr.py:339-346, calls FR per level):
-// the levels that qualify for the TMA-staged path (points == 1, W % 4 == 0) share ONE launch; the others take the per-level
+// the levels that qualify for the TMA-staged path (W % 4 == 0, a band fits) share ONE launch; the others take the per-level
 // kernels.  features / best_rbboxes / outputs / Hs / Ws / scales: HOST arrays of nlevels (<= 8) entries.
 JDET_API int jdet_feature_refine_multi(const float* const* features, const float* const* best_rbboxes, int nlevels, int N, int C,
                                        const int* Hs, const int* Ws, const float* scales, int points, float* const* outputs,
@@ -423,32 +683,15 @@ JDET_API int jdet_feature_refine_multi(const float* const* features, const float
       (points != 1 && points != 5))
     return JDET_ERR_BAD_ARG;
   if (N > 65535) return JDET_ERR_UNSUPPORTED;
-  fr_tma::FrLevels L{};
-  L.C = C;
-  long long items = 0;
-  size_t smem = 0;
+  static const bool no_staged_p5 = getenv("JDET_FR_P5_GATHER") != nullptr;
+  if (points == 1) return fr_multi<1>(features, best_rbboxes, nlevels, N, C, Hs, Ws, scales, outputs, stream);
+  if (!no_staged_p5) return fr_multi<5>(features, best_rbboxes, nlevels, N, C, Hs, Ws, scales, outputs, stream);
   for (int l = 0; l < nlevels; l++) {
     if (Hs[l] < 0 || Ws[l] < 0) return JDET_ERR_BAD_ARG;
-    if ((size_t)N * C * Hs[l] * Ws[l] == 0) continue;
-    if (!features[l] || !best_rbboxes[l] || !outputs[l]) return JDET_ERR_BAD_ARG;
-    fr_tma::FrLevel v;
-    if (points == 1 && fr_tma_config(features[l], N, C, Hs[l], Ws[l], nlevels, &v)) {
-      v.feat = features[l]; v.boxes = best_rbboxes[l]; v.out = outputs[l]; v.scale = scales[l]; v.item_begin = (int)items;
-      items += (long long)v.bands * v.chunks * N;
-      smem = std::max(smem, (size_t)v.stages * (v.rows + 2 * fr_tma::kHalo) * v.W * 4 + 2 * fr_tma::kMaxStages * sizeof(uint64_t));
-      L.lv[L.n++] = v;
-    } else {
-      const int e = jdet_feature_refine(features[l], best_rbboxes[l], N, C, Hs[l], Ws[l], points, scales[l], outputs[l], stream);
-      if (e) return e;
-    }
+    const int e = jdet_feature_refine(features[l], best_rbboxes[l], N, C, Hs[l], Ws[l], points, scales[l], outputs[l], stream);
+    if (e) return e;
   }
-  if (L.n == 0) return 0;
-  if (items > 0x7fffffffLL) return JDET_ERR_UNSUPPORTED;
-  using namespace fr_tma;
-  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_multi_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(feature_refine_tma_multi_kernel<1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  feature_refine_tma_multi_kernel<1, 4><<<(int)items, kConsumers + 32, smem, (cudaStream_t)stream>>>(L);
-  return (int)cudaGetLastError();
+  return 0;
 }
 
 // backward of jdet_feature_refine w.r.t. features: FeatureRefineFunction.grad (ops/fr.py:266-271, 242-252)

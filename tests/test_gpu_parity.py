@@ -1163,6 +1163,35 @@ def test_full_size_cfg4_level0():
 
 
 @pytest.mark.parametrize("points", [1, 5])
+def test_feature_refine_staged_bands_vs_oracle(points):
+    """cfg4 level-0 geometry (128 x 128: 16 row bands, first / interior / last) on a few channels: the staged kernels' halo, zero
+    pad and clamped last row / column, the refined anchors' corner samples leaving the map on every side"""
+    rng = np.random.default_rng(40 + points)
+    N, C, H, W, stride = 1, 12, 128, 128, 8.0
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    boxes = s2anet_anchors(rng, N, H, W, stride)[..., [1, 0, 2, 3, 4]].copy()
+    boxes[0, 64, 10:20, 2:4] *= 5                                # corners beyond the 8 halo rows: the global-tap path
+    boxes[0, :, W - 1, 1] = (W - 1) * stride + 3.0               # centres between the last column and the map's edge (clamped taps)
+    boxes[0, H - 1, :, 0] = (H - 1) * stride + 5.0
+    got = ops().fr.feature_refine(cu(x), cu(boxes), 1 / stride, points).cpu().numpy()
+    want = oracle.feature_refine(x, boxes, 1 / stride, points)
+    assert np.abs(got - want).max() <= TOL, np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("points", [1, 5])
+@pytest.mark.parametrize("hw", [(1, 8), (2, 4), (3, 12), (40, 4)])
+def test_feature_refine_tiny_maps(points, hw):
+    """maps of one or two rows / four columns: every sample is clamped onto the last row or column"""
+    H, W = hw
+    rng = np.random.default_rng(H * 100 + W + points)
+    x = rng.standard_normal((2, 5, H, W)).astype(np.float32)
+    boxes = s2anet_anchors(rng, 2, H, W, 8.0)[..., [1, 0, 2, 3, 4]].copy()
+    got = ops().fr.feature_refine(cu(x), cu(boxes), 1 / 8.0, points).cpu().numpy()
+    want = oracle.feature_refine(x, boxes, 1 / 8.0, points)
+    assert np.abs(got - want).max() <= TOL, np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("points", [1, 5])
 def test_feature_refine_multi_level_equals_per_level(points):
     """jdet_feature_refine_multi (staged levels share one launch; W % 4 != 0 levels fall back) == per-level feature_refine, bit for bit"""
     rng = np.random.default_rng(30 + points)

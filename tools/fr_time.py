@@ -36,4 +36,11 @@ def t(fn, k=20):
     return tot / k
 
 
-print("points=1 %.4f ms   points=5 %.4f ms" % (t(lambda: run(1)), t(lambda: run(5))), flush=True)
+def multi(points):
+    return ops.fr.feature_refine_multi(xs, bs, [1.0 / s for _, s in levels], points)
+
+
+print("per-level calls: points=1 %.4f ms   points=5 %.4f ms" % (t(lambda: run(1)), t(lambda: run(5))), flush=True)
+print("one call       : points=1 %.4f ms   points=5 %.4f ms" % (t(lambda: multi(1)), t(lambda: multi(5))), flush=True)
+print("level 0 alone  : points=5 %.4f ms" % t(lambda: ops.fr.feature_refine(xs[0], bs[0], 1.0 / 8, 5)), flush=True)
+print("JDET_FR_P5_GATHER=%s" % os.environ.get("JDET_FR_P5_GATHER"), flush=True)
