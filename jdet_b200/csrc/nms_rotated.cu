@@ -40,12 +40,14 @@ constexpr int kMaskThreads = 256;
 #define JDET_NMS_MASK_MINB 3
 #endif
 constexpr int kQCap = JDET_NMS_QCAP;   // survivor queue entries per CTA (overflow => extra rounds)
+constexpr int kSplitTile = 512;        // boxes per CTA of the class split (256 threads x 2: 196 CTAs at 100k boxes)
 
 struct NmsWs {
   unsigned* keys_in; unsigned* keys_out; int* vals_in; int* vals_out;
   BoxRec* rec; int* sorted_idx; int* flags; int* flag_scan; int* seg_start;
   int* seg_items; int* item_base; long long* seg_tiles; long long* tile_base;
-  int* counters;                   // [0] work counter; bytes 8..15: the 64-bit candidate-queue reservation count
+  int* counters;                   // [0] work counter; bytes 8..15: the 64-bit candidate-queue reservation count; [8]: split tiles done
+  unsigned char* keys8; int* tile_hist; int* tile_off; int* key_base;   // class split: key per box, per-tile key counts / offsets, first slot per key
   uint4* xqueue; int xcap;         // device-wide exact-IoU candidate queue
   unsigned long long* mask; size_t mask_tiles;
   void* cub_temp; size_t cub_bytes;
@@ -68,6 +70,10 @@ static size_t carve(NmsWs* w, void* base, int n) {
   w->seg_items = (int*)take(n1 * 4);     w->item_base = (int*)take(n1 * 4);
   w->seg_tiles = (long long*)take(n1 * 8); w->tile_base = (long long*)take(n1 * 8);
   w->counters = (int*)take(256);
+  w->keys8 = (unsigned char*)take(n1);
+  w->tile_hist = (int*)take((size_t)jdet_ceil_div(n, kSplitTile) * 256 * 4);
+  w->tile_off = (int*)take((size_t)jdet_ceil_div(n, kSplitTile) * 256 * 4);
+  w->key_base = (int*)take(256 * 4);
   w->cub_bytes = (size_t)n * 16 + (1u << 20);
   w->cub_temp = take(w->cub_bytes);
   w->xcap = (int)(((long long)n * n / 2 < (8ll << 20)) ? ((long long)n * n / 2 + 64) : (8ll << 20));
@@ -126,6 +132,11 @@ __host__ __device__ __forceinline__ long long items_prefix(long long m) {
   return (long long)kCH * q * (q + 1) / 2 + r * (q + 1);
 }
 
+__device__ __forceinline__ int items_prefix32(int m) {   // the same in 32 bits (m <= 23438 column blocks: n <= 1.5 M)
+  const int q = m / kCH, r = m % kCH;
+  return (kCH / 2) * q * (q + 1) + r * (q + 1);
+}
+
 __global__ void seg_count_kernel(const int* __restrict__ seg_start, const int* __restrict__ scan, int n,
                                  int* __restrict__ seg_items, long long* __restrict__ seg_tiles) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,6 +150,133 @@ __global__ void seg_count_kernel(const int* __restrict__ seg_start, const int* _
     tiles = W * (W + 1) / 2;
   }
   seg_items[s] = items; seg_tiles[s] = tiles;
+}
+
+// ---- class split: score order -> per-class segments, score order kept inside a class --------------------------------
+// Two launches instead of key + radix sort (3) + gather + 3 device scans (6) + 2 segment kernels, whose ~60 us were launch
+// latency on 100k boxes: a stable one-pass multi-split on the 8-bit grouping key.
+//   split_count_kernel    per tile of 2048 boxes (in score order): the key of every box, the tile's key histogram; the LAST
+//                         tile to finish turns the histograms into per-(tile, key) output bases and writes the segment
+//                         tables the mask / scan kernels read (seg_start, item_base, tile_base, segment count)
+//   split_scatter_kernel  per tile: the stable rank of every box among its tile's boxes of the same key (warp match +
+//                         counters per (round, warp, key)), then rec / sorted_idx at base + rank
+__global__ void __launch_bounds__(256) split_count_kernel(const float* __restrict__ dets, const int* __restrict__ order, int n, int ntiles,
+                                                          unsigned char* __restrict__ keys8, int* __restrict__ tile_hist,
+                                                          int* __restrict__ tile_off, int* __restrict__ key_base, int* __restrict__ counters, int* __restrict__ seg_start,
+                                                          int* __restrict__ item_base, long long* __restrict__ tile_base,
+                                                          int* __restrict__ nseg_out, unsigned char* __restrict__ keep) {
+  __shared__ int s_hist[256];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  s_hist[tid] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSplitTile / 256; r++) {
+    const int i = tile * kSplitTile + r * 256 + tid;
+    if (i < n) {
+      const unsigned k = label_key(dets[(size_t)order[i] * 6 + 5]);
+      keys8[i] = (unsigned char)k;
+      keep[i] = 0;                                       // (the scan kernel sets the kept ones)
+      atomicAdd(&s_hist[k], 1);
+    }
+  }
+  __syncthreads();
+  tile_hist[(size_t)tile * 256 + tid] = s_hist[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(counters + 8, 1) == ntiles - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last tile: thread k owns key k
+  // tile_off[t][key] = boxes of this key in the tiles before t.  32 loads are issued before the first store: ptxas keeps
+  // these GPU-scope loads behind earlier stores, and one L2 round trip per tile made this tail 49 us at 196 tiles
+  int run = 0;
+  for (int t0 = 0; t0 < ntiles; t0 += 32) {
+    int c[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) c[j] = t0 + j < ntiles ? __ldcg(tile_hist + (size_t)(t0 + j) * 256 + tid) : 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      if (t0 + j < ntiles) tile_off[(size_t)(t0 + j) * 256 + tid] = run;
+      run += c[j];
+    }
+  }
+  __shared__ int s_a[256], s_seg[256];
+  __shared__ long long s_t[256];
+  s_a[tid] = run;                                        // boxes of key tid
+  __syncthreads();
+  int key_start = 0, seg = 0;
+  for (int k = 0; k < tid; k++) { key_start += s_a[k]; seg += s_a[k] > 0; }     // 256 x 256 adds: nothing
+  key_base[tid] = key_start;                             // first output slot of key tid
+  const long long Wk = (run + 63) / 64;
+  __syncthreads();                                       // everyone has read the counts
+  s_seg[tid] = run > 0 ? seg : -1;
+  s_a[tid] = run > 0 ? (int)items_prefix(Wk) : 0;        // work items / mask tiles of this key's segment
+  s_t[tid] = run > 0 ? Wk * (Wk + 1) / 2 : 0;
+  if (run > 0) seg_start[seg] = key_start;
+  __syncthreads();
+  if (run > 0) {
+    int ib = 0; long long tb = 0;
+    for (int k = 0; k < tid; k++) { ib += s_a[k]; tb += s_t[k]; }
+    item_base[seg] = ib; tile_base[seg] = tb;
+  }
+  if (tid == 255) {
+    int ib = 0, ns = 0; long long tb = 0;
+    for (int k = 0; k < 256; k++) { ib += s_a[k]; tb += s_t[k]; ns += s_seg[k] >= 0; }
+    seg_start[ns] = n; item_base[ns] = ib; tile_base[ns] = tb;
+    *nseg_out = ns;
+  }
+}
+
+__global__ void __launch_bounds__(256) split_scatter_kernel(const float* __restrict__ dets, const int* __restrict__ order, int n,
+                                                            const unsigned char* __restrict__ keys8, const int* __restrict__ tile_off,
+                                                            const int* __restrict__ key_base,
+                                                            BoxRec* __restrict__ rec, int* __restrict__ sorted_idx) {
+  constexpr int R = kSplitTile / 256;
+  __shared__ unsigned short s_cnt[R][8][256];            // boxes of (round, warp) with this key -> exclusive prefix in (round, warp) order
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = blockIdx.x;
+  for (int i = tid; i < R * 8 * 256; i += 256) (&s_cnt[0][0][0])[i] = 0;
+  __syncthreads();
+  unsigned key[R];
+  int lrank[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i = tile * kSplitTile + r * 256 + tid;
+    key[r] = i < n ? (unsigned)keys8[i] : 256u + (unsigned)lane;      // absent boxes match nobody
+    const unsigned m = __match_any_sync(0xffffffffu, key[r]);
+    lrank[r] = __popc(m & ((1u << lane) - 1u));
+    if (i < n && lrank[r] == 0) s_cnt[r][warp][key[r]] = (unsigned short)__popc(m);
+  }
+  __syncthreads();
+  {
+    unsigned run = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+      for (int w = 0; w < 8; w++) { const unsigned c = s_cnt[r][w][tid]; s_cnt[r][w][tid] = (unsigned short)run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i = tile * kSplitTile + r * 256 + tid;
+    if (i >= n) continue;
+    const int pos = key_base[key[r]] + tile_off[(size_t)tile * 256 + key[r]] + s_cnt[r][warp][key[r]] + lrank[r];
+    const int src = order[i];
+    const float* b = dets + (size_t)src * 6;
+    rec[pos] = make_rec(b[0], b[1], b[2], b[3], b[4], b[5], false, true);
+    sorted_idx[pos] = src;
+  }
+}
+
+// one segment (box_length 5, or the thr < 0 corner): the tables the class split writes otherwise
+__global__ void single_segment_kernel(int n, int* __restrict__ seg_start, int* __restrict__ item_base, long long* __restrict__ tile_base,
+                                      int* __restrict__ nseg_out) {
+  const long long W = (n + 63) / 64;
+  seg_start[0] = 0; seg_start[1] = n;
+  item_base[0] = 0; item_base[1] = (int)items_prefix(W);
+  tile_base[0] = 0; tile_base[1] = W * (W + 1) / 2;
+  *nseg_out = 1;
 }
 
 // Mask layout: per segment, upper-triangular 64x64 tiles in COLUMN-block-major order, so the scan
@@ -165,31 +303,43 @@ __global__ void __launch_bounds__(kMaskThreads, JDET_NMS_MASK_MINB) nms_mask_ker
   unsigned* s_bits = reinterpret_cast<unsigned*>(s_rowq + 64);            //  4 KB: tile words as (lo, hi)
   unsigned short* s_q1 = reinterpret_cast<unsigned short*>(s_bits + kCH * 64 * 2);   // 2 x kQCap entries
   unsigned short* s_q2 = s_q1 + kQCap;
-  __shared__ int s_cnt1, s_cnt2, s_item;
+  __shared__ int s_cnt1, s_cnt2, s_item, s_seg, s_rb, s_cb0;
   __shared__ unsigned long long s_xbase;   // 64-bit: a dense same-class cluster of ~65k boxes reserves more than 2^31 candidates
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int nseg = scan[n - 1];
   const int total = item_base[nseg];
 
+  int next_item = 0;                                     // (warp 0) fetched one item ahead: the atomic's round trip is off the path
+  if (tid == 0) next_item = atomicAdd(counter, 1);
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_item = atomicAdd(counter, 1);
+    if (tid < 32) {
+      // item -> (segment, row block, first column block): two binary searches, done by ONE warp in 32-bit arithmetic
+      // (n <= 1.5 M: F(W) < 2^25); every warp decoding its own copy in 64 bits was 12 % of the kernel's instructions
+      const int item = __shfl_sync(0xffffffffu, next_item, 0);
+      if (lane == 0) next_item = atomicAdd(counter, 1);
+      int seg = 0, rb = 0, cb0 = 0;
+      if (item < total) {
+        int lo = 0, hi = nseg;                           // item_base[lo] <= item < item_base[hi]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (item_base[mid] <= item) lo = mid; else hi = mid; }
+        seg = lo;
+        const int W = (seg_start[seg + 1] - seg_start[seg] + 63) >> 6;
+        const int local = item - item_base[seg];
+        const int FW = items_prefix32(W);
+        int rlo = 0, rhi = W;                            // cum(rb) = F(W) - F(W - rb) <= local
+        while (rhi - rlo > 1) { const int mid = (rlo + rhi) >> 1; if (FW - items_prefix32(W - mid) <= local) rlo = mid; else rhi = mid; }
+        rb = rlo;
+        cb0 = rb + (local - (FW - items_prefix32(W - rb))) * kCH;
+      }
+      if (lane == 0) { s_item = item; s_seg = seg; s_rb = rb; s_cb0 = cb0; }
+    }
     __syncthreads();
     const int item = s_item;
     if (item >= total) break;
-    int lo = 0, hi = nseg;                               // item_base[lo] <= item < item_base[hi]
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (item_base[mid] <= item) lo = mid; else hi = mid; }
-    const int seg = lo;
+    const int seg = s_seg, rb = s_rb, cb0 = s_cb0;
     const int s0 = seg_start[seg], cnt = seg_start[seg + 1] - s0;
     const int W = (cnt + 63) >> 6;
-    const long long local = item - item_base[seg];
-    const long long FW = items_prefix(W);
-    int rlo = 0, rhi = W;                                // cum(rb) = F(W) - F(W - rb) <= local
-    while (rhi - rlo > 1) { const int mid = (rlo + rhi) >> 1; if (FW - items_prefix(W - mid) <= local) rlo = mid; else rhi = mid; }
-    const int rb = rlo;
-    const int chunk = (int)(local - (FW - items_prefix(W - rb)));
-    const int cb0 = rb + chunk * kCH;
     const int ncb = min(kCH, W - cb0);
     const int ncols = ncb * 64;
 
@@ -507,10 +657,19 @@ JDET_API int jdet_nms_rotated_ex(const float* dets, int n, int box_length, const
   const int flags = label_in_pair | (convention == 0 ? 2 : 0) | (getenv("JDET_NMS_NO_PRUNE") ? 4 : 0);
   const bool segment = (box_length == 6) && !label_in_pair;
 
-  JDET_RETURN_IF_CUDA(cudaMemsetAsync(keep, 0, (size_t)n, st));
   JDET_RETURN_IF_CUDA(cudaMemsetAsync(w.counters, 0, 256, st));
-  const int* pos = nullptr;
-  if (segment) {
+  static const bool legacy_split = getenv("JDET_NMS_LEGACY_SPLIT") != nullptr;   // A/B: the radix-sort + device-scan segment build
+  if (segment && !legacy_split) {
+    const int ntiles = jdet_ceil_div(n, kSplitTile);
+    split_count_kernel<<<ntiles, 256, 0, st>>>(dets, order, n, ntiles, w.keys8, w.tile_hist, w.tile_off, w.key_base, w.counters, w.seg_start, w.item_base,
+                                               w.tile_base, w.flag_scan + (n - 1), keep);
+    split_scatter_kernel<<<ntiles, 256, 0, st>>>(dets, order, n, w.keys8, w.tile_off, w.key_base, w.rec, w.sorted_idx);
+  } else if (!segment) {
+    JDET_RETURN_IF_CUDA(cudaMemsetAsync(keep, 0, (size_t)n, st));
+    gather_kernel<<<G, T, 0, st>>>(dets, box_length, order, nullptr, w.keys_out, n, label_in_pair, w.rec, w.sorted_idx, w.flags);
+    single_segment_kernel<<<1, 1, 0, st>>>(n, w.seg_start, w.item_base, w.tile_base, w.flag_scan + (n - 1));
+  } else {
+    JDET_RETURN_IF_CUDA(cudaMemsetAsync(keep, 0, (size_t)n, st));
     key_kernel<<<G, T, 0, st>>>(dets, order, n, w.keys_in, w.vals_in);
     size_t need = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, w.keys_in, w.keys_out, w.vals_in, w.vals_out, n, 0, 8, st);
@@ -518,21 +677,16 @@ JDET_API int jdet_nms_rotated_ex(const float* dets, int n, int box_length, const
     need = w.cub_bytes;
     JDET_RETURN_IF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_temp, need, w.keys_in, w.keys_out, w.vals_in,
                                                        w.vals_out, n, 0, 8, st));
-    pos = w.vals_out;
-  }
-  gather_kernel<<<G, T, 0, st>>>(dets, box_length, order, pos, w.keys_out, n, label_in_pair, w.rec,
-                                 w.sorted_idx, w.flags);
-  {
-    size_t need = 0;
+    gather_kernel<<<G, T, 0, st>>>(dets, box_length, order, w.vals_out, w.keys_out, n, label_in_pair, w.rec,
+                                   w.sorted_idx, w.flags);
+    need = 0;
     cub::DeviceScan::InclusiveSum(nullptr, need, w.flags, w.flag_scan, n, st);
     if (need > w.cub_bytes) return JDET_ERR_WORKSPACE;
     need = w.cub_bytes;
     JDET_RETURN_IF_CUDA(cub::DeviceScan::InclusiveSum(w.cub_temp, need, w.flags, w.flag_scan, n, st));
-  }
-  seg_start_kernel<<<G, T, 0, st>>>(w.flags, w.flag_scan, n, w.seg_start);
-  seg_count_kernel<<<G, T, 0, st>>>(w.seg_start, w.flag_scan, n, w.seg_items, w.seg_tiles);
-  {
-    size_t need = w.cub_bytes;
+    seg_start_kernel<<<G, T, 0, st>>>(w.flags, w.flag_scan, n, w.seg_start);
+    seg_count_kernel<<<G, T, 0, st>>>(w.seg_start, w.flag_scan, n, w.seg_items, w.seg_tiles);
+    need = w.cub_bytes;
     JDET_RETURN_IF_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, need, w.seg_items, w.item_base, n + 1, st));
     need = w.cub_bytes;
     JDET_RETURN_IF_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, need, w.seg_tiles, w.tile_base, n + 1, st));
