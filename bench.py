@@ -200,14 +200,16 @@ def run_ours(args):
     roofline = {"bound": "hbm",
                 "kernel": "roi_align_rotated = roi_prologue_kernel<1> (re-layout + tap tables + cost buckets) + roi_gather_kernel<16, true> "
                           "(2 kernel launches + one 256-B memset node per step; the duration used is the WHOLE step, dominant "
-                          "kernel = the gather, ~69 % of it: 71.9 of 103.4 us in the ncu launch list, profiles/r01_launches_reentry.md)",
+                          "kernel = the gather, ~69 % of it: 72.5 of 104.6 us in the ncu launch list, profiles/r02_launches_bench.md)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "peak_source": peaks["source"], "algorithmic_bytes": alg_bytes,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels from the committed ncu --set full
-                # capture (profiles/r01_ncu_reentry_selected_metrics.csv, cold L2): prologue 67.2 + 31.7 MB, gather 114.1 + 53.0 MB
+                # captures, cold L2.  Round 1 (profiles/r01_ncu_reentry_selected_metrics.csv): prologue 67.2 + 31.7 MB, gather
+                # 114.1 + 53.0 MB = 266 MB; round 2 (profiles/r02_ncu_selected_metrics.csv): 67.2 + 0.03 and 113.6 + 0.06 MB —
+                # the same reads, the written lines still in L2 when each kernel ends.  The larger figure is reported.
                 "traffic": 266_000_000,
-                "note": "latency-bound, no unit saturated (ncu: l1tex 43-53 %, issue slots 47 %, 43 % of stall samples wait on "
-                        "loads, L1 hit 45-58 %, DRAM 33 %): 0.80 GB of merged taps cross L1 per launch for 170 MB of algorithmic "
+                "note": "latency-bound, no unit saturated (ncu round 2: gather l1tex 57 %, issue slots 39 %, L1 hit 57 %, 0.41 GB "
+                        "L2 -> L1; prologue issue 58 %): 0.80 GB of merged taps cross L1 per launch for 170 MB of algorithmic "
                         "bytes; an L2-resident random 1-KB gather probe reaches 19-20 TB/s on this GPU "
                         "(profiles/r01_l2_gather_probe.txt)"}
 
