@@ -212,7 +212,22 @@ constexpr int kMaxStages = 8;
 
 // the geometry of one instantiation: CW consumer warps, PPT pixels per consumer thread, HALO staged rows either side of the band
 template <int POINTS> struct Geo;
-template <> struct Geo<1> { static constexpr int CW = 8, PPT = 4, HALO = 4, MINB = 3; };   // 3 CTAs per SM: 72 registers
+#ifndef JDET_FR1_CW          // A/B switches, as for points = 5 below
+#define JDET_FR1_CW 8
+#endif
+#ifndef JDET_FR1_PPT
+#define JDET_FR1_PPT 4
+#endif
+#ifndef JDET_FR1_HALO
+#define JDET_FR1_HALO 4
+#endif
+#ifndef JDET_FR1_MINB
+#define JDET_FR1_MINB 3      // 3 CTAs per SM: 72 registers
+#endif
+#ifndef JDET_FR1_SMEM_KB
+#define JDET_FR1_SMEM_KB 64
+#endif
+template <> struct Geo<1> { static constexpr int CW = JDET_FR1_CW, PPT = JDET_FR1_PPT, HALO = JDET_FR1_HALO, MINB = JDET_FR1_MINB; };
 // points = 5: HALO bounds the stage (rows_per_band + 2 * HALO rows); the rows actually staged are those the band's samples read
 // (fr_tma_body<5>: 21 of the 32-row capacity on average at cfg4's 128 x 128 level, whose 4-cell anchors' corners reach +-9 rows)
 #ifndef JDET_FR5_CW          // A/B switches (tools/ab_libs.py build NAME=flags:-DJDET_FR5_CW=8 -DJDET_FR5_PPT=4 ...)
@@ -234,7 +249,7 @@ template <> struct Geo<5> { static constexpr int CW = JDET_FR5_CW, PPT = JDET_FR
 // floats per stage: the band, then (points = 5) a zero pad of one row + 8 words that no copy ever writes: a sample outside the
 // map reads its 2 x 2 taps there (see fr_tma_body<5>)
 template <int POINTS>
-__host__ __device__ constexpr int fr_zero_pad(int W) { return POINTS == 5 ? W + 8 : 0; }
+__host__ __device__ constexpr int fr_zero_pad(int W) { return W + 8; }
 template <int POINTS>
 __host__ __device__ constexpr int fr_stage_elems(int rows_per_band, int W) {
   return (rows_per_band + 2 * Geo<POINTS>::HALO) * W + fr_zero_pad<POINTS>(W);
@@ -291,14 +306,9 @@ struct FrRing {
 };
 constexpr size_t kRingTail = 2 * kMaxStages * sizeof(uint64_t) + 16;             // barriers + span
 
-template <int POINTS>
-__device__ __forceinline__ void fr_tma_body(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
-                                            float spatial_scale, int rows_per_band, int ch_per_cta, int stages,
-                                            float* __restrict__ out, int band, int chunk, int n);
-
-// points = 1
-template <>
-__device__ __forceinline__ void fr_tma_body<1>(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
+// points = 1, first form (kept for A/B, -DJDET_FR1_LEGACY): four tap offsets + four weights per pixel in registers, a
+// staged-or-global branch per sample — 42 instructions per pixel-channel, 71 % of the issue slots at 4.3 TB/s
+__device__ __forceinline__ void fr_tma_body1_legacy(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
                                                float spatial_scale, int rows_per_band, int ch_per_cta, int stages,
                                                float* __restrict__ out, int band, int chunk, int n) {
   constexpr int POINTS = 1, PPT = Geo<1>::PPT, kConsumers = Geo<1>::CW * 32;
@@ -386,16 +396,19 @@ __device__ __forceinline__ void fr_tma_body<1>(const float* __restrict__ feat, c
 // L1 gather takes 0.68 ms).  A sample outside the map points at the stage's zero pad (contributes the reference's exact 0;
 // finite features assumed: a non-finite value in the column / row next to a clamped tap would turn its 0 weight into NaN).
 // A thread with a sample outside the staged rows (0.02 % at cfg4) walks its pixels' taps from a local-memory table, all from global.
-template <>
-__device__ __forceinline__ void fr_tma_body<5>(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
-                                               float spatial_scale, int rows_per_band, int ch_per_cta, int stages,
-                                               float* __restrict__ out, int band, int chunk, int n) {
-  constexpr int POINTS = 5, PPT = Geo<5>::PPT, kConsumers = Geo<5>::CW * 32, kHalo = Geo<5>::HALO;
+template <int POINTS>
+__device__ __forceinline__ void fr_tma_body(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
+                                            float spatial_scale, int rows_per_band, int ch_per_cta, int stages,
+                                            float* __restrict__ out, int band, int chunk, int n) {
+#ifdef JDET_FR1_LEGACY
+  if (POINTS == 1) { fr_tma_body1_legacy(feat, boxes, C, H, W, spatial_scale, rows_per_band, ch_per_cta, stages, out, band, chunk, n); return; }
+#endif
+  constexpr int PPT = Geo<POINTS>::PPT, kConsumers = Geo<POINTS>::CW * 32, kHalo = Geo<POINTS>::HALO;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = H * W;
   const int c0 = chunk * ch_per_cta, c1 = min(C, c0 + ch_per_cta);
   const int r0 = band * rows_per_band, r1 = min(H, r0 + rows_per_band);
-  FrRing<5> R(smem_raw, H, W, r0, rows_per_band, stages);
+  FrRing<POINTS> R(smem_raw, H, W, r0, rows_per_band, stages);
   const int tid = threadIdx.x, lane = tid & 31;
   const int nch = c1 - c0;
   const int band_px = (r1 - r0) * W;
@@ -486,7 +499,7 @@ __device__ __forceinline__ void fr_tma_body<5>(const float* __restrict__ feat, c
           float ly = tly[j][k], lx = tlx[j][k];
           // opaque to the optimiser: without this the weights and the four offsets are hoisted out of the channel loop and
           // the 15 registers per pixel are 40 again
-          asm volatile("" : "+r"(a), "+f"(ly), "+f"(lx));
+          if (POINTS > 1) asm volatile("" : "+r"(a), "+f"(ly), "+f"(lx));   // (points = 1: 8 registers per pixel are affordable, let them be hoisted)
           const float hy = 1.f - ly, hx = 1.f - lx;
           const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
           v[j] += w1 * at(a) + w2 * at(a + 4u) + w3 * at(a + wb) + w4 * at(a + wb + 4u);
@@ -573,7 +586,7 @@ static bool fr_tma_config(const float* features, int N, int C, int H, int W, fr_
   const int rows = max(1, min(H, band_pixels / W));
   const size_t stage_bytes = (size_t)fr_stage_elems<POINTS>(rows, W) * 4;
   // points = 1: ~64 KB of copies in flight per CTA, 3 CTAs per SM; points = 5: one 17-warp CTA per SM, ~100 KB
-  int stages = (int)((POINTS == 1 ? 64 * 1024 : JDET_FR5_SMEM_KB * 1024) / stage_bytes);
+  int stages = (int)((POINTS == 1 ? JDET_FR1_SMEM_KB * 1024 : JDET_FR5_SMEM_KB * 1024) / stage_bytes);
   stages = stages > kMaxStages ? kMaxStages : stages;
   if (stages < 2) return false;
   const int bands = jdet_ceil_div(H, rows);
