@@ -29,7 +29,11 @@
 
 namespace jdet {
 
-constexpr int kTR = 64, kTC = 128, kThreads = 256;
+// Tile = TR x 128 outputs per 256-thread CTA.  TR = 64 for most sizes; 128 for the largest (A/B on one B200: 16k x 16k
+// 425 -> 404 us — the per-CTA fixed work, record loads, five barriers and the compaction scans, is shared by twice the
+// pairs — but 4k x 4k clustered 120 -> 130 us and 1k x 1k 21.5 -> 23.6 us: fewer, longer CTAs fill the machine worse).
+constexpr int kTC = 128, kThreads = 256;
+constexpr long long kBigTilePairs = 1ll << 27;
 #ifndef JDET_IOU_TILE_MINB
 #define JDET_IOU_TILE_MINB 8          // resident CTAs per SM asked of ptxas (32 registers; A/B on one B200, 16k x 16k: 4 -> 537 us, 6 -> 525, 8 -> 517)
 #endif
@@ -56,11 +60,13 @@ __global__ void __launch_bounds__(256) rec_kernel(const float* __restrict__ boxe
   *dst = make_rec(b[0], b[1], b[2], b[3], b[4], 0.f, zero_small != 0, false);
 }
 
-template <int VERSION, bool VEC4>
+template <int VERSION, bool VEC4, int kTR>
 __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(const BoxRec* __restrict__ rec1, int n1,
                                                              const BoxRec* __restrict__ rec2, int n2,
                                                              float* __restrict__ out, unsigned long long* __restrict__ gcount,
                                                              uint2* __restrict__ gqueue, int gcap, int variant) {
+  constexpr int kRPW = kTR / 8, kMasks = kRPW / 8;      // rows per warp; 32-pair masks per thread (8 rows x 4 columns each)
+  static_assert(kTR == 64 || kTR == 128, "tile rows");
   __shared__ BoxRec s_row[kTR];
   __shared__ BoxRec s_col[kTC];
   __shared__ __align__(16) float s_cx[kTC], s_cy[kTC], s_cr[kTC];
@@ -100,23 +106,26 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
   const float4 cx = reinterpret_cast<const float4*>(s_cx)[lane];
   const float4 cy = reinterpret_cast<const float4*>(s_cy)[lane];
   const float4 cr = reinterpret_cast<const float4*>(s_cr)[lane];
-  unsigned rej = 0;                                     // pair p = 4 * k + q ends up in bit 31 - p
+  unsigned rej[kMasks];                                 // mask m: pair p = 4 * (k - 8 * m) + q ends up in bit 31 - p
+#pragma unroll
+  for (int m = 0; m < kMasks; m++) rej[m] = 0u;
   {
     const int gc = col0 + 4 * lane;
-    float* o = out + (size_t)(row0 + warp * 8) * n2 + gc;
-    const int rows_left = n1 - (row0 + warp * 8);
+    float* o = out + (size_t)(row0 + warp * kRPW) * n2 + gc;
+    const int rows_left = n1 - (row0 + warp * kRPW);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const float4 rq = s_rq[warp * 8 + k];
+    for (int k = 0; k < kRPW; k++) {
+      const float4 rq = s_rq[warp * kRPW + k];
       {   // four circle tests as two packed passes (columns x|y, z|w against the broadcast row)
         const unsigned long long X1 = f2_pack(rq.x, rq.x), Y1 = f2_pack(rq.y, rq.y), Q1 = f2_pack(rq.z, rq.z);
         float t0, t1, t2, t3;
         circle_t2(X1, Y1, Q1, f2_pack(cx.x, cx.y), f2_pack(cy.x, cy.y), f2_pack(cr.x, cr.y), t0, t1);
         circle_t2(X1, Y1, Q1, f2_pack(cx.z, cx.w), f2_pack(cy.z, cy.w), f2_pack(cr.z, cr.w), t2, t3);
-        rej = __funnelshift_l(__float_as_uint(t0), rej, 1);
-        rej = __funnelshift_l(__float_as_uint(t1), rej, 1);
-        rej = __funnelshift_l(__float_as_uint(t2), rej, 1);
-        rej = __funnelshift_l(__float_as_uint(t3), rej, 1);
+        unsigned& rj = rej[k / 8];
+        rj = __funnelshift_l(__float_as_uint(t0), rj, 1);
+        rj = __funnelshift_l(__float_as_uint(t1), rj, 1);
+        rj = __funnelshift_l(__float_as_uint(t2), rj, 1);
+        rj = __funnelshift_l(__float_as_uint(t3), rj, 1);
       }
       if (k < rows_left) {
         if (VEC4) {
@@ -130,13 +139,17 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
       o += n2;
     }
   }
-  unsigned surv = __brev(~rej);                         // bit p: pair (row warp * 8 + p / 4, column 4 * lane + p % 4) survives
+  unsigned surv[kMasks];                                // mask m, bit p: pair (row warp * kRPW + 8 * m + p / 4, column 4 * lane + p % 4) survives
+#pragma unroll
+  for (int m = 0; m < kMasks; m++) surv[m] = __brev(~rej[m]);
   // Survivors -> SAT -> device-wide queue, in rounds of at most kQCap queued survivors (a tile normally has a few
   // hundred; the small queues keep 8 CTAs resident per SM, which is what hides the load -> store -> atomic latency
   // chain of these short CTAs).  Whatever does not fit stays in the per-thread masks for the next round.
   for (;;) {
     {  // compact: warp exclusive scan of popcounts, one atomic per warp
-      const int cnt = __popc(surv);
+      int cnt = 0;
+#pragma unroll
+      for (int m = 0; m < kMasks; m++) cnt += __popc(surv[m]);
       int incl = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -148,14 +161,20 @@ __global__ void __launch_bounds__(kThreads, JDET_IOU_TILE_MINB) iou_tile_kernel(
       if (lane == 31 && total > 0) base = atomicAdd(&s_cnt1, total);
       base = __shfl_sync(0xffffffffu, base, 31);
       int pos = base + incl - cnt;
-      while (surv && pos < kQCap) {
-        const int b = __ffs(surv) - 1;
-        surv &= surv - 1;
-        const int r = warp * 8 + (b >> 2), c = 4 * lane + (b & 3);
-        s_q1[pos++] = (unsigned short)((r << 7) | c);
+#pragma unroll
+      for (int m = 0; m < kMasks; m++) {
+        while (surv[m] && pos < kQCap) {
+          const int b = __ffs(surv[m]) - 1;
+          surv[m] &= surv[m] - 1;
+          const int r = warp * kRPW + 8 * m + (b >> 2), c = 4 * lane + (b & 3);
+          s_q1[pos++] = (unsigned short)((r << 7) | c);
+        }
       }
     }
-    const int pending = __syncthreads_or(surv != 0u);
+    unsigned left = 0u;
+#pragma unroll
+    for (int m = 0; m < kMasks; m++) left |= surv[m];
+    const int pending = __syncthreads_or(left != 0u);
 
     // ---- phase 2: SAT on circle survivors ----------------------------------------------------
     const int cnt1 = min(s_cnt1, kQCap);
@@ -276,20 +295,27 @@ JDET_API int jdet_box_iou_rotated_ex(const float* boxes1, int n1, const float* b
   int gcap = (int)iou_queue_cap(n1, n2);
   if (const char* e = getenv("JDET_TEST_QUEUE_CAP")) gcap = std::max(1, std::min(gcap, atoi(e)));   // tests: force the queue-full path
   rec_kernel<<<jdet_ceil_div(n1 + n2, 256), 256, 0, st>>>(boxes1, n1, boxes2, n2, version == 1, rec1, rec2, gcount);
-  dim3 grid(jdet_ceil_div(n2, kTC), jdet_ceil_div(n1, kTR));
   const bool vec = (n2 % 4 == 0) && (((uintptr_t)ious & 15) == 0);
   const long long pairs = (long long)n1 * n2;
+  const bool big = pairs >= kBigTilePairs;
+  dim3 grid(jdet_ceil_div(n2, kTC), jdet_ceil_div(n1, big ? 128 : 64));
   const int xgrid = (int)(pairs < 256 * 1024 ? (pairs + 255) / 256 : num_sms() * 8);
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(iou_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExactSmem));
   JDET_RETURN_IF_CUDA(cudaFuncSetAttribute(iou_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kExactSmem));
+#define JDET_IOU_TILE(V, VEC, TR) iou_tile_kernel<V, VEC, TR><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant)
+#define JDET_IOU_TILES(V)                                                                                              \
+  do {                                                                                                                 \
+    if (big) { if (vec) JDET_IOU_TILE(V, true, 128); else JDET_IOU_TILE(V, false, 128); }                              \
+    else     { if (vec) JDET_IOU_TILE(V, true, 64);  else JDET_IOU_TILE(V, false, 64); }                               \
+  } while (0)
   if (version == 0) {
-    if (vec) iou_tile_kernel<0, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
-    else     iou_tile_kernel<0, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
+    JDET_IOU_TILES(0);
     iou_exact_kernel<0><<<xgrid, kExactThreads, kExactSmem, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious, variant);
   } else {
-    if (vec) iou_tile_kernel<1, true><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
-    else     iou_tile_kernel<1, false><<<grid, kThreads, 0, st>>>(rec1, n1, rec2, n2, ious, gcount, gqueue, gcap, variant);
+    JDET_IOU_TILES(1);
     iou_exact_kernel<1><<<xgrid, kExactThreads, kExactSmem, st>>>(rec1, rec2, n2, gcount, gqueue, gcap, ious, variant);
   }
+#undef JDET_IOU_TILES
+#undef JDET_IOU_TILE
   return (int)cudaGetLastError();
 }
