@@ -721,16 +721,30 @@ __global__ void __launch_bounds__(256) roi_align_bwd_nhwc_kernel(const float* __
   float* base = grad_nhwc + (size_t)g.batch * H * W * C + c0;
   const int q = threadIdx.x % QL;
   const float cntf = (float)spb;                     // the backward divides by gh*gw in both versions
+  // (grad * w) / count as the reference writes it; for a power-of-two count (sampling_ratio 2: 4) the division is the exact
+  // multiplication by 2^-k — four full-precision divisions per tap were most of this loop's instructions
+  const bool pow2 = (spb & (spb - 1)) == 0;
+  const float rcnt = 1.f / cntf;
   for (int bin = threadIdx.x / QL; bin < nbins; bin += blockDim.x / QL) {
     const float4 go = make_float4(s_go[(4 * q + 0) * nbins + bin], s_go[(4 * q + 1) * nbins + bin],
                                   s_go[(4 * q + 2) * nbins + bin], s_go[(4 * q + 3) * nbins + bin]);
     const int2* e = fin + bin * tpb;
     const int n = cnt[bin];
-    for (int k = 0; k < n; k++) {
-      const int2 t = e[k];
-      const float w = __int_as_float(t.y);
-      const float4 v = make_float4(go.x * w / cntf, go.y * w / cntf, go.z * w / cntf, go.w * w / cntf);
-      atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.x * C) + q, v);
+    if (pow2) {
+      for (int k = 0; k < n; k++) {
+        const int2 t = e[k];
+        const float w = __int_as_float(t.y);
+        const float4 v = make_float4(__fmul_rn(__fmul_rn(go.x, w), rcnt), __fmul_rn(__fmul_rn(go.y, w), rcnt),
+                                     __fmul_rn(__fmul_rn(go.z, w), rcnt), __fmul_rn(__fmul_rn(go.w, w), rcnt));
+        atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.x * C) + q, v);
+      }
+    } else {
+      for (int k = 0; k < n; k++) {
+        const int2 t = e[k];
+        const float w = __int_as_float(t.y);
+        const float4 v = make_float4(go.x * w / cntf, go.y * w / cntf, go.z * w / cntf, go.w * w / cntf);
+        atomicAdd(reinterpret_cast<float4*>(base + (size_t)t.x * C) + q, v);
+      }
     }
   }
 }
