@@ -387,8 +387,11 @@ __global__ void __launch_bounds__(256) roi_prologue_kernel(const float* __restri
 // and leaves as ONE cp.async.bulk store.
 // (256, 4) / (256, 3): without a blocks-per-SM hint ptxas squeezes the kernel into 32 registers by sinking every load
 // next to its FMAs; 64 registers (80 for the two-bins-per-warp form) keep the 8 loads of a step in flight.
+#ifndef JDET_ROI_PAIR_MINB
+#define JDET_ROI_PAIR_MINB 3
+#endif
 template <int QL, bool PAIR>
-__global__ void __launch_bounds__(256, PAIR ? 3 : 4) roi_gather_kernel(const __grid_constant__ RoiLevels L,
+__global__ void __launch_bounds__(256, PAIR ? JDET_ROI_PAIR_MINB : 4) roi_gather_kernel(const __grid_constant__ RoiLevels L,
                                                              const unsigned char* __restrict__ tables, size_t stride, int C,
                                                              int nbins, int nslabs, int R, uint32_t rec_bytes, int fin_off, int items_known,
                                                              int* __restrict__ work_counter, float* __restrict__ out) {
@@ -930,7 +933,7 @@ static cudaError_t launch_gather(const RoiLevels& L, int B, const unsigned char*
   const uint32_t rec_bytes = (uint32_t)RL.cnpx_off;                  // header, cnt, fin
   const size_t smem = (((size_t)cfg.slab * (nbins | 1) + 3) & ~(size_t)3) * 4 + 2 * (size_t)rec_bytes;
   const bool pair = cfg.slab == 128;   // two bins per warp (A/B on one box, cfg2 whole op: 116.8 vs 122.1 us)
-  const int lgrid = (int)std::min<long long>((long long)R * nslabs, (long long)sms * (pair ? 3 : 4));
+  const int lgrid = (int)std::min<long long>((long long)R * nslabs, (long long)sms * (pair ? JDET_ROI_PAIR_MINB : 4));
 #define JDET_LAUNCH_ROI(QL_, PAIR_)                                                                                    \
   do {                                                                                                                 \
     if (smem > 48 * 1024) { cudaError_t e_ = cudaFuncSetAttribute(roi_gather_kernel<QL_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e_ != cudaSuccess) return e_; } \
