@@ -19,7 +19,7 @@ def install_as_jdet():
     for sub in ("ops", "ops.box_iou_rotated", "ops.box_iou_rotated_v1", "ops.nms_rotated", "ops.roi_align_rotated",
                 "ops.roi_align_rotated_v1", "ops.fr", "ops.dcn_v1", "ops.orn", "ops.bbox_transforms", "models", "models.roi_heads",
                 "models.roi_heads.s2anet_head", "models.roi_extractors", "models.boxes",
-                "models.boxes.iou_calculator"):
+                "models.boxes.iou_calculator", "data", "data.devkits", "data.devkits.result_merge", "data.devkits.dota_utils"):
         try:
             sys.modules.setdefault("jdet." + sub, importlib.import_module(__name__ + "." + sub))
         except ImportError:

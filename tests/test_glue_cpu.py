@@ -110,3 +110,50 @@ def test_argsort_key_treats_signed_zero_as_one_score():
     s = np.array([0.0, -0.0, 0.5, -0.0, 0.0], np.float32)
     order = np.argsort(-np.where(s == 0, 0.0, s), kind="stable")
     assert order.tolist() == [2, 0, 1, 3, 4]
+
+
+# ------------------------------------------------------------------------------------ tile -> image merge (result_merge.py)
+def _write_result_file(path, rows):
+    with open(path, "w") as f:
+        for name, score, poly in rows:
+            f.write(name + " " + repr(float(score)) + " " + " ".join(repr(float(v)) for v in poly) + "\n")
+
+
+def test_result_merge_parsing_grouping_and_output_format(tmp_path):
+    """jdet.data.devkits.result_merge mirror: tile names -> (image, scale, offset), poly2origpoly, grouping, the output lines —
+    with a stand-in NMS (no GPU here)."""
+    from jdet_b200.data.devkits import dota_utils as util
+    from jdet_b200.data.devkits import result_merge as rm
+    assert rm.poly2origpoly([1, 2, 3, 4, 5, 6, 7, 8], 100, 200, "0.5") == [202.0, 404.0, 206.0, 408.0, 210.0, 412.0, 214.0, 416.0]
+    src, dst = tmp_path / "raw", tmp_path / "merged"
+    src.mkdir(); dst.mkdir()
+    rows = [("P0001__1__0___0", 0.9, [10, 10, 20, 10, 20, 20, 10, 20]),
+            ("P0001__1__512___1024", 0.8, [1, 2, 3, 2, 3, 4, 1, 4]),
+            ("P0002__0.5__100___0", 0.7, [0, 0, 8, 0, 8, 8, 0, 8]),
+            ("P0001__1__0___0", 0.6, [11, 10, 21, 10, 21, 20, 11, 20])]
+    _write_result_file(src / "Task1_plane.txt", rows)
+    assert util.custombasename(str(src / "Task1_plane.txt")) == "Task1_plane"
+    assert util.GetFileFromThisRootDir(str(src)) == [str(src / "Task1_plane.txt")]
+    parsed = rm.parse_result_file(str(src / "Task1_plane.txt"))
+    assert list(parsed) == ["P0001", "P0002"] and len(parsed["P0001"]) == 3
+    assert parsed["P0001"][1] == [513.0, 1026.0, 515.0, 1026.0, 515.0, 1028.0, 513.0, 1028.0, 0.8]
+    assert parsed["P0002"][0] == [200.0, 0.0, 216.0, 0.0, 216.0, 16.0, 200.0, 16.0, 0.7]
+    seen = []
+
+    def keep_all_reversed(dets, thresh):
+        seen.append((dets.shape, thresh))
+        return list(range(len(dets)))[::-1]
+
+    rm.mergesingle(str(dst), keep_all_reversed, str(src / "Task1_plane.txt"))
+    assert seen == [((3, 9), rm.nms_threshold_0), ((1, 9), rm.nms_threshold_0)]
+    lines = open(dst / "Task1_plane.txt").read().splitlines()
+    assert lines[0] == "P0001 0.6 11.0 10.0 21.0 10.0 21.0 20.0 11.0 20.0"
+    assert lines[3] == "P0002 0.7 200.0 0.0 216.0 0.0 216.0 16.0 200.0 16.0" and len(lines) == 4
+    # per-class thresholds (the reference's cfg.merge_nms_threshold_type == 1)
+    _write_result_file(src / "plane.txt", rows[:1])
+    seen.clear()
+    rm.mergesingle(str(dst), keep_all_reversed, str(src / "plane.txt"), nms_threshold_type=1)
+    assert seen == [((1, 9), rm.nms_threshold_1["plane"])]
+    import jdet_b200
+    jdet_b200.install_as_jdet()
+    from jdet.data.devkits.result_merge import mergebypoly, mergebyobb, mergebyrec   # noqa: F401  (reference import paths)

@@ -1201,3 +1201,47 @@ def test_feature_refine_multi_level_equals_per_level(points):
     multi = ops().fr.feature_refine_multi(xs, bs, [1.0 / st for _, _, st in shapes], points)
     for x, b, (_, _, st), o in zip(xs, bs, shapes, multi):
         assert torch.equal(o, ops().fr.feature_refine(x, b, 1.0 / st, points))
+
+
+# ------------------------------------------------------------------------------------ tile -> image merge
+@pytest.mark.gpu
+def test_result_merge_files_match_the_oracle(tmp_path):
+    """mergebypoly / mergebyobb on result files of overlapping tiles == the same merge with the oracle's NMS, line for line"""
+    from oracle import glue
+    from jdet_b200.data.devkits import result_merge as rm
+    from jdet_b200.models.boxes import rotated_box_to_poly
+    rng = np.random.default_rng(77)
+    src = tmp_path / "raw"; src.mkdir()
+    names = ["Task1_plane", "Task1_ship"]
+    for name in names:
+        rows = []
+        for img in ("P0001", "P0007"):
+            boxes = clustered_boxes(rng, 240, 6, 700.0)                       # image coordinates; duplicates = objects seen by two tiles
+            polys = rotated_box_to_poly(torch.as_tensor(boxes)).numpy().astype(np.float64)
+            scores = tie_free_scores(rng, len(boxes))
+            for p, s in zip(polys, scores):
+                tx, ty = int(rng.integers(0, 2)) * 512, int(rng.integers(0, 2)) * 512
+                tile = "%s__1__%d___%d" % (img, tx, ty)
+                rows.append((tile, s, [round(float(v - (tx, ty)[i & 1]), 1) for i, v in enumerate(p)]))
+        with open(src / (name + ".txt"), "w") as f:
+            for tile, s, p in rows:
+                f.write(tile + " " + repr(float(s)) + " " + " ".join(repr(v) for v in p) + "\n")
+    for merge, tag in ((rm.mergebypoly, "poly"), (rm.mergebyobb, "obb")):
+        dst = tmp_path / ("merged_" + tag); dst.mkdir()
+        merge(str(src), str(dst))
+        for name in names:
+            parsed = rm.parse_result_file(str(src / (name + ".txt")))
+            want = []
+            for img, dets in parsed.items():
+                d = np.array(dets)
+                if tag == "poly":
+                    keep = glue.py_cpu_nms_poly_fast(d.astype(np.float32).astype(np.float64), 0.1)
+                else:
+                    from jdet_b200.models.boxes.coder import rectpoly2obb
+                    b = rectpoly2obb(torch.as_tensor(d[:, :8], dtype=torch.float32)).numpy()
+                    order = oracle.argsort_desc(d[:, 8].astype(np.float32))
+                    keep = np.nonzero(oracle.nms_rotated_keep(b, order, 0.1, oracle.VARIANT_CPU))[0]
+                want += [img + " " + str(dets[int(i)][-1]) + " " + " ".join(map(str, dets[int(i)][:-1])) for i in keep]
+            got = open(dst / (name + ".txt")).read().splitlines()
+            assert got == want, (tag, name, len(got), len(want))
+            assert 0 < len(got) < sum(len(v) for v in parsed.values())
