@@ -1245,3 +1245,28 @@ def test_result_merge_files_match_the_oracle(tmp_path):
             got = open(dst / (name + ".txt")).read().splitlines()
             assert got == want, (tag, name, len(got), len(want))
             assert 0 < len(got) < sum(len(v) for v in parsed.values())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("points", [1, 5])
+def test_feature_refine_fuzz_shapes_and_boxes(points):
+    """random map shapes (staged and unstaged widths, one-row maps, bands that end mid-stage), boxes from sub-pixel to larger than
+    the map, centres far (and absurdly far) outside it: staged kernels == oracle"""
+    rng = np.random.default_rng(900 + points)
+    for case in range(28):
+        N, C = int(rng.integers(1, 4)), int(rng.integers(1, 10))
+        H = int(rng.integers(1, 72))
+        W = int(rng.integers(1, 40)) * 4 if case % 4 else int(rng.integers(1, 70))
+        stride = float(rng.choice([4.0, 8.0, 16.0]))
+        x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+        boxes = s2anet_anchors(rng, N, H, W, stride)[..., [1, 0, 2, 3, 4]].copy()
+        boxes[..., 2:4] *= np.exp(rng.uniform(-3, 3, boxes[..., 2:4].shape)).astype(np.float32)      # 1/20 x ... 20 x the anchor
+        far = rng.random(boxes.shape[:3]) < 0.03
+        boxes[far, 0:2] += rng.uniform(-3, 3, (int(far.sum()), 2)).astype(np.float32) * stride * max(H, W)
+        bad = rng.random(boxes.shape[:3]) < 0.01
+        boxes[bad, int(rng.integers(0, 2))] = rng.choice([1e30, -1e30, 3e9])     # (NaN / Inf coordinates index out of bounds in the reference: undefined there)
+        got = ops().fr.feature_refine(cu(x), cu(boxes), 1 / stride, points).cpu().numpy()
+        want = oracle.feature_refine(x, boxes, 1 / stride, points)
+        ok = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), ok), (case, H, W)
+        assert np.abs(got[ok] - want[ok]).max(initial=0.0) <= TOL, (case, N, C, H, W, np.abs(got[ok] - want[ok]).max())
