@@ -246,8 +246,8 @@ template <> struct Geo<1> { static constexpr int CW = JDET_FR1_CW, PPT = JDET_FR
 #define JDET_FR5_MINB 1
 #endif
 template <> struct Geo<5> { static constexpr int CW = JDET_FR5_CW, PPT = JDET_FR5_PPT, HALO = JDET_FR5_HALO, MINB = JDET_FR5_MINB; };
-// floats per stage: the band, then (points = 5) a zero pad of one row + 8 words that no copy ever writes: a sample outside the
-// map reads its 2 x 2 taps there (see fr_tma_body<5>)
+// floats per stage: the band, then a zero pad of one row + 8 words that no copy ever writes: a sample outside the map reads its
+// 2 x 2 taps there (see fr_tma_body)
 template <int POINTS>
 __host__ __device__ constexpr int fr_zero_pad(int W) { return W + 8; }
 template <int POINTS>
@@ -255,19 +255,13 @@ __host__ __device__ constexpr int fr_stage_elems(int rows_per_band, int W) {
   return (rows_per_band + 2 * Geo<POINTS>::HALO) * W + fr_zero_pad<POINTS>(W);
 }
 
-// CTA = CW consumer warps + 1 producer warp; grid = (row bands, channel chunks, N).  A band is CW*32*PPT / W
-// full-width rows (+ HALO rows either side): contiguous in an NCHW plane, so one cp.async.bulk per channel
-// stages it.  The producer lane only waits on empty[] and issues copies; the consumers never block on a
-// refill, and `stages` channels per CTA x the CTAs of the SM are in flight.  Each consumer thread owns PPT
-// pixels (rows CW*32/W apart): their POINTS tap sets and weights live in registers for the whole channel walk;
-// a sample whose taps leave the staged rows reads them from global.
-//
-// points = 5 (21 shared-memory reads per pixel-channel): a thread whose samples are all staged (or outside the map: those point
-// at the stage's zero word with zero weights, contributing the reference's exact 0) runs a branch-free body, so its 42 reads
-// are issued back to back; per-sample branches (each a read -> FMA round trip) made the first version of this path
-// latency-bound at 1.14 ms where the L1 gather took 0.68 ms.
+// CTA = CW consumer warps + 1 producer warp; work item = (row band, channel chunk, image).  A band is CW*32*PPT / W full-width
+// rows plus the rows above and below that its samples read (at most HALO either side): contiguous in an NCHW plane, so ONE
+// cp.async.bulk per channel stages it.  The producer lane only waits on empty[] and issues copies; the consumers never block
+// on a refill, and `stages` channels per CTA x the CTAs of the SM are in flight.  Each consumer thread owns PPT pixels (rows
+// CW*32/W apart) and keeps their samples in registers for the whole channel walk (fr_tma_body).
 // shared-memory ring of one CTA: `stages` bands of stage_elems floats, then the full[] / empty[] barriers and two words
-// (points = 5: the first / last row the band's samples touch)
+// (the first / last row the band's samples touch)
 template <int POINTS>
 struct FrRing {
   float* ring; uint64_t* full; uint64_t* empty; int* span;
@@ -387,15 +381,21 @@ __device__ __forceinline__ void fr_tma_body1_legacy(const float* __restrict__ fe
   }
 }
 
-// points = 5: 21 shared-memory reads per pixel-channel.  What bounds it is shared-memory wavefronts (the corners of independent
-// boxes land in arbitrary banks: ~2.5 wavefronts per read), so issue slots are plentiful and registers are what is scarce: a sample
-// is kept as ONE word (byte offset of its top-left tap inside the stage) plus its two
-// lerp fractions, and the four weights are re-formed per channel exactly as fr.py:57-63 forms them — 15 registers per pixel
-// instead of 40, which leaves the compiler room to issue a pixel's 21 reads back to back (with the taps in 80 registers and a
-// per-sample staged-or-global branch the first version of this path serialised read -> FMA -> read and ran at 1.14 ms where the
-// L1 gather takes 0.68 ms).  A sample outside the map points at the stage's zero pad (contributes the reference's exact 0;
-// finite features assumed: a non-finite value in the column / row next to a clamped tap would turn its 0 weight into NaN).
-// A thread with a sample outside the staged rows (0.02 % at cfg4) walks its pixels' taps from a local-memory table, all from global.
+// The consumer body for both point counts.  A sample is kept as ONE word (byte offset of its top-left tap inside the stage) plus
+// its two lerp fractions; the 2 x 2 taps are read at +0, +4, +row, +row + 4 and the four weights formed as fr.py:57-63 forms them.
+//   * Where the reference clamps the lower / right neighbour onto the tap itself (last row / column: fraction exactly 0) the cell
+//     is moved one row / column back with fraction exactly 1 — the same two products in the same order, every read inside the
+//     map.  A sample outside the map points at the stage's zero pad and contributes the reference's exact 0.
+//   * The rows staged per band are those its samples touch (CTA-wide min / max before the first copy), up to the stage's
+//     capacity; a thread with a sample beyond that (none at cfg4) reads its taps from global memory out of a local-memory table.
+//   * points = 5 (21 shared-memory reads per pixel-channel) is bound by shared-memory wavefronts — the corners of independent
+//     boxes land in arbitrary banks, ~2.5 wavefronts per read — so issue slots are plentiful and registers scarce: the weights
+//     are RE-formed per channel (an empty asm stops the optimiser hoisting them: 15 registers per pixel instead of 40), which
+//     lets a pixel's 21 reads issue back to back.  With 40 registers per pixel and a staged-or-global branch per sample the first
+//     version of this path serialised read -> FMA -> read and ran at 1.14 ms where the L1 gather takes 0.68 ms; now 0.35 ms.
+//   * points = 1 (5 reads) is an HBM stream; its weights and offsets are hoisted (8 registers per pixel), and the branch-free
+//     body costs 15 instructions per pixel-channel where the first form (fr_tma_body1_legacy) cost 42: 0.087 -> 0.076 ms.
+// (Finite features assumed: a non-finite value next to a clamped tap would turn its 0 weight into NaN.)
 template <int POINTS>
 __device__ __forceinline__ void fr_tma_body(const float* __restrict__ feat, const float* __restrict__ boxes, int C, int H, int W,
                                             float spatial_scale, int rows_per_band, int ch_per_cta, int stages,
