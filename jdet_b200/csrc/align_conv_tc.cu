@@ -29,6 +29,7 @@
 //
 // Layout in HBM: x (N,C,H,W) fp32 -> channel-last scratch (N,H,W,C); anchors (N,H,W,5); weight
 // (Co,C,3,3) -> scratch [9*C/16][Co][16] hi and lo (swizzled); out (N,Co,H,W).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace jdet {
@@ -81,6 +82,39 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: the leader issues M = 256 MMAs over both CTAs' A tiles and B halves
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {     // the barrier at the same offset in CTA `cta`
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope (remote arrivals)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {                           // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -149,10 +183,18 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
   lo[dst] = l;
 }
 
+// NCTA = 1: one CTA per tile (M = 128).  NCTA = 2: a CTA pair per two tiles — each CTA produces its own 128 A rows and loads
+// HALF of the weights of a K block; the leader's MMAs (cta_group::2, M = 256) read both CTAs' shared memory, so the weight
+// stream into each SM is halved (at level 0 the kernel moves 8.3 GB from L2 into the SMs, 4.8 GB of it weights: l1tex 79 %).
+template <int NCTA>
 __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid_constant__ Params p) {
+  constexpr int kStages = NCTA == 2 ? 6 : tc::kStages;
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const int pair_id = (int)blockIdx.x / NCTA, npairs = (int)gridDim.x / NCTA;
+  const int num_pairs = (p.num_tiles + NCTA - 1) / NCTA;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_bytes = p.Co * kRowBytes;
+  const int b_bytes = p.Co * kRowBytes / NCTA;         // this CTA's share of a K block's weights (per term)
   const int stage_bytes = 2 * kABytes + 2 * b_bytes;
   auto a_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return smem + (size_t)s * stage_bytes + kABytes; };
@@ -163,23 +205,30 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
   uint64_t* empty = bars + kStages;      // [kStages]
   uint64_t* tfull = bars + 2 * kStages;  // [2]
   uint64_t* tempty = bars + 2 * kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* pfull = bars + 2 * kStages + 4;      // [kStages] (pair leader only): the peer CTA's stage is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cblocks = p.C / kBlockK;
   const int num_kb = 9 * cblocks;
 
   if (warp == kLoadWarp && lane == 0) {
-    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], kProdWarps + 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], kProdWarps + 1); mbar_init(&empty[s], 1); mbar_init(&pfull[s], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * NCTA); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) cluster_sync_all();                 // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -187,10 +236,13 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
     // =============================== A producers ==============================================
     const int pw = warp - 4, sp = lane / kQuads, q = lane % kQuads;
     uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int pr = pair_id; pr < num_pairs; pr += npairs) {
+      const int tile_raw = pr * NCTA + (int)cta_rank;
+      const bool dummy = tile_raw >= p.num_tiles;      // the odd tile out of a pair: zeros in, nothing out
+      const int tile = dummy ? p.num_tiles - 1 : tile_raw;
       const Level& L = p.lv[level_of(p, tile)];
       const int HW = L.H * L.W;
-      const long long P = (long long)p.N * HW;
+      const long long P = dummy ? 0 : (long long)p.N * HW;
       const int ltile = tile - L.tile_begin;
       // per-pixel anchor geometry (s2anet_head.py:689-698), 8 pixels per lane
       float gx[kPix], gy[kPix], gdw[kPix], gdh[kPix], gc[kPix], gs[kPix], fh[kPix], fw[kPix];
@@ -291,12 +343,13 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
     // =============================== B loader ==================================================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const size_t my_half = (size_t)cta_rank * (p.Co / NCTA) * kBlockK;     // this CTA's output channels of a K block
+      for (int pr = pair_id; pr < num_pairs; pr += npairs) {
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], 2u * (uint32_t)b_bytes);
-          bulk_g2s(b_hi(stage), p.b_hi + (size_t)kb * p.Co * kBlockK, (uint32_t)b_bytes, &full[stage]);
-          bulk_g2s(b_lo(stage), p.b_lo + (size_t)kb * p.Co * kBlockK, (uint32_t)b_bytes, &full[stage]);
+          bulk_g2s(b_hi(stage), p.b_hi + (size_t)kb * p.Co * kBlockK + my_half, (uint32_t)b_bytes, &full[stage]);
+          bulk_g2s(b_lo(stage), p.b_lo + (size_t)kb * p.Co * kBlockK + my_half, (uint32_t)b_bytes, &full[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -304,14 +357,26 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer =================================================
     // instruction descriptor: D=F32, A=B=TF32, K-major both, N = Co, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)((kBlockM * NCTA) >> 4) << 24);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
+    if (NCTA == 2 && cta_rank != 0) {
+      // the peer's MMA warp only relays: "my stage is complete" (A rows produced, weight half landed) -> the leader
+      for (int pr = pair_id; pr < num_pairs; pr += npairs) {
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(&full[stage], phase);
+          if (lane == 0) { fence_proxy_async(); mbar_arrive_remote(&pfull[stage], 0u); }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else
+    for (int pr = pair_id; pr < num_pairs; pr += npairs) {
+      if (NCTA == 2) mbar_wait_cluster(&tempty[acc], acc_phase ^ 1); else mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co;
       for (int kb = 0; kb < num_kb; kb++) {
         mbar_wait(&full[stage], phase);
+        if (NCTA == 2) mbar_wait_cluster(&pfull[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint64_t ah = make_desc(smem_u32(a_hi(stage))), al = make_desc(smem_u32(a_lo(stage)));
@@ -319,12 +384,23 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
 #pragma unroll
           for (int kk = 0; kk < kBlockK / 8; kk++) {
             const uint64_t adv = (uint64_t)(kk * 2);     // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle row
-            tc_mma_tf32(d_tmem, al + adv, bh + adv, idesc, (kb | kk) ? 1u : 0u);   // small terms first
-            tc_mma_tf32(d_tmem, ah + adv, bl + adv, idesc, 1u);
-            tc_mma_tf32(d_tmem, ah + adv, bh + adv, idesc, 1u);
+            if (NCTA == 2) {
+              tc_mma_tf32_2(d_tmem, al + adv, bh + adv, idesc, (kb | kk) ? 1u : 0u);
+              tc_mma_tf32_2(d_tmem, ah + adv, bl + adv, idesc, 1u);
+              tc_mma_tf32_2(d_tmem, ah + adv, bh + adv, idesc, 1u);
+            } else {
+              tc_mma_tf32(d_tmem, al + adv, bh + adv, idesc, (kb | kk) ? 1u : 0u);   // small terms first
+              tc_mma_tf32(d_tmem, ah + adv, bl + adv, idesc, 1u);
+              tc_mma_tf32(d_tmem, ah + adv, bh + adv, idesc, 1u);
+            }
           }
-          tc_commit(&empty[stage]);                       // frees the smem stage when these MMAs retire
-          if (kb == num_kb - 1) tc_commit(&tfull[acc]);   // accumulator complete
+          if (NCTA == 2) {
+            tc_commit2(&empty[stage]);                      // frees the stage in both CTAs
+            if (kb == num_kb - 1) tc_commit2(&tfull[acc]);
+          } else {
+            tc_commit(&empty[stage]);                       // frees the smem stage when these MMAs retire
+            if (kb == num_kb - 1) tc_commit(&tfull[acc]);   // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -334,12 +410,15 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
   } else {
     // =============================== epilogue (warps 0-3) ======================================
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int pr = pair_id; pr < num_pairs; pr += npairs) {
+      const int tile_raw = pr * NCTA + (int)cta_rank;
+      const bool dummy = tile_raw >= p.num_tiles;
+      const int tile = dummy ? p.num_tiles - 1 : tile_raw;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const Level& L = p.lv[level_of(p, tile)];
       const int HW = L.H * L.W;
-      const long long P = (long long)p.N * HW;
+      const long long P = dummy ? 0 : (long long)p.N * HW;
       const int r = warp * 32 + lane;
       const long long pix = (long long)(tile - L.tile_begin) * kBlockM + r;
       const bool ok = pix < P;
@@ -366,16 +445,18 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) { if (NCTA == 2) mbar_arrive_remote(&tempty[acc], 0u); else mbar_arrive(&tempty[acc]); }   // (the leader waits for both CTAs' epilogues)
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (NCTA == 2) cluster_sync_all();                 // nobody leaves while the pair still reads its shared memory / barriers
   if (warp == kMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -417,12 +498,28 @@ int align_conv_tc_launch_multi(const float* const* xs, const float* const* ancho
   if (p.num_tiles == 0) return 0;
   const long long wt = (long long)Co * C * 9;
   weight_prep_kernel<<<(int)((wt + 255) / 256), 256, 0, st>>>(weight, Co, C, b_hi, b_lo);
-  const size_t smem = 1024 + (size_t)kStages * (2 * kABytes + 2 * (size_t)Co * kRowBytes) + 256;
-  cudaError_t e = cudaFuncSetAttribute(align_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
   const int sms = num_sms();
+  static const bool pair = getenv("JDET_ALIGN_CONV_2CTA") != nullptr;      // opt-in: CTA pairs (cta_group::2)
+  if (pair && Co % 64 == 0 && p.num_tiles >= 2) {
+    const size_t smem = 1024 + (size_t)6 * (2 * kABytes + (size_t)Co * kRowBytes) + 512;
+    cudaError_t e = cudaFuncSetAttribute(align_conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int pairs = (p.num_tiles + 1) / 2;
+    const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, align_conv_tc_kernel<2>, p);
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+  }
+  const size_t smem = 1024 + (size_t)kStages * (2 * kABytes + 2 * (size_t)Co * kRowBytes) + 256;
+  cudaError_t e = cudaFuncSetAttribute(align_conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  align_conv_tc_kernel<<<grid, kThreads, smem, st>>>(p);
+  align_conv_tc_kernel<1><<<grid, kThreads, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 

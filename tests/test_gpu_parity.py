@@ -16,6 +16,7 @@ from _inputs import ADVERSARIAL, clustered_boxes, dota_boxes, s2anet_anchors, ti
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOL = 1e-4   # abs tolerance for sampled features / IoU floats (north_star)
 
 
@@ -1270,3 +1271,44 @@ def test_feature_refine_fuzz_shapes_and_boxes(points):
         ok = np.isfinite(want)
         assert np.array_equal(np.isfinite(got), ok), (case, H, W)
         assert np.abs(got[ok] - want[ok]).max(initial=0.0) <= TOL, (case, N, C, H, W, np.abs(got[ok] - want[ok]).max())
+
+
+@pytest.mark.gpu
+def test_align_conv_cta_pair_variant_is_bit_identical():
+    """JDET_ALIGN_CONV_2CTA=1 (tcgen05 cta_group::2: M = 256 MMAs over a CTA pair, half the weights per CTA) == the default kernel,
+    bit for bit, on a multi-level call with an odd tile count (one dummy tile in the last pair).  The switch is read once per
+    process, so the variant runs in a child process."""
+    import hashlib
+    import subprocess
+    import sys
+    code = r'''
+import hashlib, os, sys
+import numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+from jdet_b200.models.roi_heads.s2anet_head import AlignConv
+from _inputs import s2anet_anchors
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(4)
+levels = [(24, 8), (12, 16), (5, 32)]
+g = torch.Generator(device=dev).manual_seed(9)
+xs = [torch.randn((3, 64, h, h + 4), device=dev, generator=g) for h, _ in levels]
+an = [torch.as_tensor(s2anet_anchors(rng, 3, h, h + 4, s)).to(dev) for h, s in levels]
+torch.manual_seed(2)
+ac = AlignConv(64, 128, 3).to(dev).requires_grad_(False)
+outs = ac.forward_multi(xs, an, [s for _, s in levels])
+torch.cuda.synchronize()
+h = hashlib.sha1()
+for o in outs:
+    h.update(o.cpu().numpy().tobytes())
+print("HASH", h.hexdigest())
+''' % (ROOT, ROOT)
+    hashes = []
+    for pair in (False, True):
+        env = dict(os.environ)
+        env.pop("JDET_ALIGN_CONV_2CTA", None)
+        if pair:
+            env["JDET_ALIGN_CONV_2CTA"] = "1"
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        hashes.append([l for l in out.stdout.splitlines() if l.startswith("HASH")][0])
+    assert hashes[0] == hashes[1]
