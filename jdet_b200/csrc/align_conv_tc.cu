@@ -270,10 +270,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
           pbase[it] = -1;
         }
       }
-      for (int t = 0; t < 9; t++) {
-        // tap geometry once per tap, reused by the C/32 channel blocks
-        int o00[kPix], o01[kPix], o10[kPix], o11[kPix];
-        float w1[kPix], w2[kPix], w3[kPix], w4[kPix];
+      // tap geometry once per tap, reused by the C/16 channel blocks
+      int o00[kPix], o01[kPix], o10[kPix], o11[kPix];
+      float w1[kPix], w2[kPix], w3[kPix], w4[kPix];
+      auto tap_geometry = [&](int t) {
         const float xx = (float)(t % 3 - 1), yy = (float)(t / 3 - 1);
 #pragma unroll
         for (int it = 0; it < kPix; it++) {
@@ -298,28 +298,45 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
             if (hh <= L.H - 1 && wh <= L.W - 1) o11[it] = hh * L.W + wh;
           }
         }
-        for (int cb = 0; cb < cblocks; cb++) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          unsigned char* ah = a_hi(stage);
-          unsigned char* al = a_lo(stage);
-          float4 v[kPix];
+      };
+        // The four corner loads of channel block cb + 1 are issued BEFORE the wait for its stage: a stage's gathers could
+        // otherwise only start once the MMAs released it, which ties the loads in flight to the ring depth (4 stages of
+        // 48 KB is all that fits) — one more K block per lane rides in registers instead.
+        float4 ca[kPix], cb4[kPix], cc[kPix], cd[kPix];
+        auto gather = [&](int cbk, float4 (&a)[kPix], float4 (&b)[kPix], float4 (&c)[kPix], float4 (&d)[kPix]) {
 #pragma unroll
           for (int it = 0; it < kPix; it++) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 a = z, b = z, c = z, d = z;
+            a[it] = z; b[it] = z; c[it] = z; d[it] = z;
             if (pbase[it] >= 0) {
-              const float* base = L.x_nhwc + (size_t)cb * kBlockK + q * 4;
+              const float* base = L.x_nhwc + (size_t)cbk * kBlockK + q * 4;
               const size_t pb = (size_t)pbase[it];
-              if (o00[it] >= 0) a = __ldg(reinterpret_cast<const float4*>(base + (pb + o00[it]) * p.C));
-              if (o01[it] >= 0) b = __ldg(reinterpret_cast<const float4*>(base + (pb + o01[it]) * p.C));
-              if (o10[it] >= 0) c = __ldg(reinterpret_cast<const float4*>(base + (pb + o10[it]) * p.C));
-              if (o11[it] >= 0) d = __ldg(reinterpret_cast<const float4*>(base + (pb + o11[it]) * p.C));
+              if (o00[it] >= 0) a[it] = __ldg(reinterpret_cast<const float4*>(base + (pb + o00[it]) * p.C));
+              if (o01[it] >= 0) b[it] = __ldg(reinterpret_cast<const float4*>(base + (pb + o01[it]) * p.C));
+              if (o10[it] >= 0) c[it] = __ldg(reinterpret_cast<const float4*>(base + (pb + o10[it]) * p.C));
+              if (o11[it] >= 0) d[it] = __ldg(reinterpret_cast<const float4*>(base + (pb + o11[it]) * p.C));
             }
+          }
+        };
+      for (int t = 0; t < 9; t++) {
+        tap_geometry(t);
+        gather(0, ca, cb4, cc, cd);
+        for (int cb = 0; cb < cblocks; cb++) {
+          float4 v[kPix];
+#pragma unroll
+          for (int it = 0; it < kPix; it++) {
+            const float4 a = ca[it], b = cb4[it], c = cc[it], d = cd[it];
             v[it].x = w1[it] * a.x + w2[it] * b.x + w3[it] * c.x + w4[it] * d.x;
             v[it].y = w1[it] * a.y + w2[it] * b.y + w3[it] * c.y + w4[it] * d.y;
             v[it].z = w1[it] * a.z + w2[it] * b.z + w3[it] * c.z + w4[it] * d.z;
             v[it].w = w1[it] * a.w + w2[it] * b.w + w3[it] * c.w + w4[it] * d.w;
           }
+          // (carrying the prefetch across the tap boundary as well — one flat loop over the 9 * C/16 K blocks — measured
+          //  slower: 1.15 vs 1.04 ms)
+          if (cb + 1 < cblocks) gather(cb + 1, ca, cb4, cc, cd);      // in flight across the wait below
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* ah = a_hi(stage);
+          unsigned char* al = a_lo(stage);
 #pragma unroll
           for (int it = 0; it < kPix; it++) {
             const int r = pw * (kPixPerStep * kPix) + it * kPixPerStep + sp;
