@@ -46,7 +46,12 @@ constexpr int kProdWarps = 16;                // A-producer warps
 constexpr int kPix = 128 / (kProdWarps * kPixPerStep);  // pixels per lane per stage
 constexpr int kMmaWarp = 4 + kProdWarps, kLoadWarp = 5 + kProdWarps;
 constexpr int kThreads = (6 + kProdWarps) * 32;
-constexpr int kStages = 4;
+#ifndef JDET_AC_A_STAGES
+#define JDET_AC_A_STAGES 4
+#endif
+#ifndef JDET_AC_B_STAGES
+#define JDET_AC_B_STAGES 4
+#endif
 constexpr int kBlockM = 128;
 constexpr int kABytes = kBlockM * kRowBytes;   // 8 KB per term
 
@@ -188,32 +193,37 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
 // stream into each SM is halved (at level 0 the kernel moves 8.3 GB from L2 into the SMs, 4.8 GB of it weights: l1tex 79 %).
 template <int NCTA>
 __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid_constant__ Params p) {
-  constexpr int kStages = NCTA == 2 ? 6 : tc::kStages;
+  // separate rings for the two operands: an A stage is 16 KB, a B stage 2 * Co * 64 B (32 KB at Co = 256, per CTA half of it in a
+  // pair) — the gathers behind A are what needs depth, and 4 whole 48 KB stages were all that fitted
+  constexpr int kAS = NCTA == 2 ? 6 : JDET_AC_A_STAGES, kBS = NCTA == 2 ? 6 : JDET_AC_B_STAGES;
   const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const int pair_id = (int)blockIdx.x / NCTA, npairs = (int)gridDim.x / NCTA;
   const int num_pairs = (p.num_tiles + NCTA - 1) / NCTA;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.Co * kRowBytes / NCTA;         // this CTA's share of a K block's weights (per term)
-  const int stage_bytes = 2 * kABytes + 2 * b_bytes;
-  auto a_hi = [&](int s) { return smem + (size_t)s * stage_bytes; };
-  auto a_lo = [&](int s) { return smem + (size_t)s * stage_bytes + kABytes; };
-  auto b_hi = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * kABytes; };
-  auto b_lo = [&](int s) { return smem + (size_t)s * stage_bytes + 2 * kABytes + b_bytes; };
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + kStages;      // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;  // [2]
-  uint64_t* tempty = bars + 2 * kStages + 2;
-  uint64_t* pfull = bars + 2 * kStages + 4;      // [kStages] (pair leader only): the peer CTA's stage is complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
+  unsigned char* b_ring = smem + (size_t)kAS * 2 * kABytes;
+  auto a_hi = [&](int s) { return smem + (size_t)s * 2 * kABytes; };
+  auto a_lo = [&](int s) { return smem + (size_t)s * 2 * kABytes + kABytes; };
+  auto b_hi = [&](int s) { return b_ring + (size_t)s * 2 * b_bytes; };
+  auto b_lo = [&](int s) { return b_ring + (size_t)s * 2 * b_bytes + b_bytes; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)kBS * 2 * b_bytes);
+  uint64_t* afull = bars;                        // [kAS]  the producers' rows are in place
+  uint64_t* aempty = bars + kAS;                 // [kAS]  the MMAs reading the stage have retired
+  uint64_t* bfull = bars + 2 * kAS;              // [kBS]  the weight block has landed
+  uint64_t* bempty = bars + 2 * kAS + kBS;       // [kBS]
+  uint64_t* tfull = bars + 2 * kAS + 2 * kBS;    // [2]
+  uint64_t* tempty = tfull + 2;
+  uint64_t* pfull = tfull + 4;                   // [kAS] (pair leader only): the peer CTA's K block is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull + kAS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cblocks = p.C / kBlockK;
   const int num_kb = 9 * cblocks;
 
   if (warp == kLoadWarp && lane == 0) {
-    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], kProdWarps + 1); mbar_init(&empty[s], 1); mbar_init(&pfull[s], 1); }
+    for (int s = 0; s < kAS; s++) { mbar_init(&afull[s], kProdWarps); mbar_init(&aempty[s], 1); mbar_init(&pfull[s], 1); }
+    for (int s = 0; s < kBS; s++) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
     for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * NCTA); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -318,6 +328,9 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
             }
           }
         };
+      // (K order: tap outer, channel block inner.  The other order — the 9 taps of one 16-channel block back to back, for L1
+      //  reuse between the taps of neighbouring anchors — measured slower, 1.25-1.40 vs 1.03 ms: the tap geometry then sits
+      //  in front of every K block's gathers.)
       for (int t = 0; t < 9; t++) {
         tap_geometry(t);
         gather(0, ca, cb4, cc, cd);
@@ -331,10 +344,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
             v[it].z = w1[it] * a.z + w2[it] * b.z + w3[it] * c.z + w4[it] * d.z;
             v[it].w = w1[it] * a.w + w2[it] * b.w + w3[it] * c.w + w4[it] * d.w;
           }
-          // (carrying the prefetch across the tap boundary as well — one flat loop over the 9 * C/16 K blocks — measured
-          //  slower: 1.15 vs 1.04 ms)
           if (cb + 1 < cblocks) gather(cb + 1, ca, cb4, cc, cd);      // in flight across the wait below
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait(&aempty[stage], phase ^ 1);
           unsigned char* ah = a_hi(stage);
           unsigned char* al = a_lo(stage);
 #pragma unroll
@@ -351,8 +362,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
           }
           fence_proxy_async();             // generic-proxy stores -> visible to the tensor-core (async) proxy
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (lane == 0) mbar_arrive(&afull[stage]);
+          if (++stage == kAS) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -363,11 +374,11 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
       const size_t my_half = (size_t)cta_rank * (p.Co / NCTA) * kBlockK;     // this CTA's output channels of a K block
       for (int pr = pair_id; pr < num_pairs; pr += npairs) {
         for (int kb = 0; kb < num_kb; kb++) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], 2u * (uint32_t)b_bytes);
-          bulk_g2s(b_hi(stage), p.b_hi + (size_t)kb * p.Co * kBlockK + my_half, (uint32_t)b_bytes, &full[stage]);
-          bulk_g2s(b_lo(stage), p.b_lo + (size_t)kb * p.Co * kBlockK + my_half, (uint32_t)b_bytes, &full[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          mbar_wait(&bempty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bfull[stage], 2u * (uint32_t)b_bytes);
+          bulk_g2s(b_hi(stage), p.b_hi + (size_t)kb * p.Co * kBlockK + my_half, (uint32_t)b_bytes, &bfull[stage]);
+          bulk_g2s(b_lo(stage), p.b_lo + (size_t)kb * p.Co * kBlockK + my_half, (uint32_t)b_bytes, &bfull[stage]);
+          if (++stage == kBS) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -375,15 +386,17 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
     // =============================== MMA issuer =================================================
     // instruction descriptor: D=F32, A=B=TF32, K-major both, N = Co, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)((kBlockM * NCTA) >> 4) << 24);
-    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    uint32_t stage = 0, phase = 0, bstage = 0, bphase = 0, acc = 0, acc_phase = 0;
     if (NCTA == 2 && cta_rank != 0) {
       // the peer's MMA warp only relays: "my stage is complete" (A rows produced, weight half landed) -> the leader
       for (int pr = pair_id; pr < num_pairs; pr += npairs) {
         for (int kb = 0; kb < num_kb; kb++) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&afull[stage], phase);
+          mbar_wait(&bfull[bstage], bphase);
           if (lane == 0) { fence_proxy_async(); mbar_arrive_remote(&pfull[stage], 0u); }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kAS) { stage = 0; phase ^= 1; }
+          if (++bstage == kBS) { bstage = 0; bphase ^= 1; }
         }
       }
     } else
@@ -392,12 +405,13 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co;
       for (int kb = 0; kb < num_kb; kb++) {
-        mbar_wait(&full[stage], phase);
+        mbar_wait(&bfull[bstage], bphase);
+        mbar_wait(&afull[stage], phase);
         if (NCTA == 2) mbar_wait_cluster(&pfull[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint64_t ah = make_desc(smem_u32(a_hi(stage))), al = make_desc(smem_u32(a_lo(stage)));
-          const uint64_t bh = make_desc(smem_u32(b_hi(stage))), bl = make_desc(smem_u32(b_lo(stage)));
+          const uint64_t bh = make_desc(smem_u32(b_hi(bstage))), bl = make_desc(smem_u32(b_lo(bstage)));
 #pragma unroll
           for (int kk = 0; kk < kBlockK / 8; kk++) {
             const uint64_t adv = (uint64_t)(kk * 2);     // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzle row
@@ -412,15 +426,18 @@ __global__ void __launch_bounds__(kThreads, 1) align_conv_tc_kernel(const __grid
             }
           }
           if (NCTA == 2) {
-            tc_commit2(&empty[stage]);                      // frees the stage in both CTAs
+            tc_commit2(&aempty[stage]);                     // frees the stages in both CTAs
+            tc_commit2(&bempty[bstage]);
             if (kb == num_kb - 1) tc_commit2(&tfull[acc]);
           } else {
-            tc_commit(&empty[stage]);                       // frees the smem stage when these MMAs retire
+            tc_commit(&aempty[stage]);                      // frees the smem stages when these MMAs retire
+            tc_commit(&bempty[bstage]);
             if (kb == num_kb - 1) tc_commit(&tfull[acc]);   // accumulator complete
           }
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == kAS) { stage = 0; phase ^= 1; }
+        if (++bstage == kBS) { bstage = 0; bphase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -518,7 +535,7 @@ int align_conv_tc_launch_multi(const float* const* xs, const float* const* ancho
   const int sms = num_sms();
   static const bool pair = getenv("JDET_ALIGN_CONV_2CTA") != nullptr;      // opt-in: CTA pairs (cta_group::2)
   if (pair && Co % 64 == 0 && p.num_tiles >= 2) {
-    const size_t smem = 1024 + (size_t)6 * (2 * kABytes + (size_t)Co * kRowBytes) + 512;
+    const size_t smem = 1024 + (size_t)6 * (2 * kABytes + (size_t)Co * kRowBytes) + 1024;
     cudaError_t e = cudaFuncSetAttribute(align_conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int pairs = (p.num_tiles + 1) / 2;
@@ -532,7 +549,7 @@ int align_conv_tc_launch_multi(const float* const* xs, const float* const* ancho
     e = cudaLaunchKernelEx(&cfg, align_conv_tc_kernel<2>, p);
     return (int)(e != cudaSuccess ? e : cudaGetLastError());
   }
-  const size_t smem = 1024 + (size_t)kStages * (2 * kABytes + 2 * (size_t)Co * kRowBytes) + 256;
+  const size_t smem = 1024 + (size_t)JDET_AC_A_STAGES * 2 * kABytes + (size_t)JDET_AC_B_STAGES * 2 * (size_t)Co * kRowBytes + 512;
   cudaError_t e = cudaFuncSetAttribute(align_conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
