@@ -138,7 +138,7 @@ int jdet_feature_refine(const float* features, const float* best_rbboxes, int N,
                         int points, float spatial_scale, float* output, void* stream);
 
 /* feature_refine on every FPN level of one head in ONE call — FeatureRefineModule.execute (ops/fr.py:331-347) applies FR level by
- * level; here the levels that qualify for the staged path (points == 1, W % 4 == 0) share one launch.  features / best_rbboxes /
+ * level; here the levels that qualify for the staged path (W % 4 == 0, a row band fits a CTA: W <= 1024) share one launch.  features / best_rbboxes /
  * outputs / Hs / Ws / scales: HOST arrays of nlevels (<= 8) entries (device pointers inside); N and C are common.          */
 int jdet_feature_refine_multi(const float* const* features, const float* const* best_rbboxes, int nlevels, int N, int C,
                               const int* Hs, const int* Ws, const float* scales, int points, float* const* outputs, void* stream);
