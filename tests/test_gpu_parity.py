@@ -1312,3 +1312,32 @@ print("HASH", h.hexdigest())
         assert out.returncode == 0, out.stderr[-2000:]
         hashes.append([l for l in out.stdout.splitlines() if l.startswith("HASH")][0])
     assert hashes[0] == hashes[1]
+
+
+@pytest.mark.gpu
+def test_result_merge_py_cpu_nms_horizontal():
+    """py_cpu_nms (result_merge.py:147-178: pixel-counting areas, x2 - x1 + 1) on the library's NMS == a numpy restatement"""
+    from jdet_b200.data.devkits import result_merge as rm
+    rng = np.random.default_rng(5)
+    n = 600
+    ctr = rng.uniform(0, 400, (n, 2))
+    wh = np.exp(rng.uniform(np.log(6), np.log(90), (n, 2)))
+    dets = np.concatenate([np.round(ctr - wh / 2), np.round(ctr + wh / 2), tie_free_scores(rng, n)[:, None]], 1).astype(np.float64)
+
+    def restated(d, thresh):                                # the reference's greedy loop, in float64
+        x1, y1, x2, y2, sc = d.T
+        areas = (x2 - x1 + 1) * (y2 - y1 + 1)
+        order = sc.argsort()[::-1]
+        keep = []
+        while order.size > 0:
+            i = order[0]
+            keep.append(int(i))
+            w = np.maximum(0.0, np.minimum(x2[i], x2[order[1:]]) - np.maximum(x1[i], x1[order[1:]]) + 1)
+            h = np.maximum(0.0, np.minimum(y2[i], y2[order[1:]]) - np.maximum(y1[i], y1[order[1:]]) + 1)
+            ovr = w * h / (areas[i] + areas[order[1:]] - w * h)
+            order = order[np.where(ovr <= thresh)[0] + 1]
+        return keep
+
+    for thr in (0.1, 0.3, 0.5):
+        got = rm.py_cpu_nms(dets, thr)
+        assert list(got) == restated(dets, thr), thr
